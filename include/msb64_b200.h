@@ -1,0 +1,159 @@
+/* msb64_b200.h -- C ABI of the B200-native MSD radix sort for 64-bit key + 64-bit rid pairs.
+ *
+ * This is the drop-in boundary for the one hot path this library replaces: the
+ * in-place MSD radix sort of the reference's msb_64.c.  Plain C, plain pointers
+ * and sizes; no torch or CUDA types in any signature (a stream is passed as
+ * void*).  The library is libmsb64_b200.so, built by
+ * inplacemsdradixsort_b200/build.py with nvcc for sm_100a only.
+ *
+ * Section 1 re-exports the reference's own public interface, unchanged
+ * (reference include/msb_64.h:36-40), so a program written against msb_64.h links
+ * against this library instead of msb_64.c and gets the same arrays back sorted.
+ * Section 2 is the same sort with explicit error codes and with device-resident
+ * data (what a GPU pipeline binds).  Section 3 holds the helpers the reference
+ * keeps beside sort() (generator, checker) in their device form.
+ *
+ * There is no CPU fallback anywhere behind these entry points: if no CUDA device
+ * is usable every int-returning function returns MSB64_ERR_CUDA, and sort()
+ * prints the error and aborts (the reference's own failure mode is assert()).
+ */
+#ifndef MSB64_B200_H_
+#define MSB64_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- 1. drop-in
+ *
+ * sort(): replaces msb_64.c:2261-2430 (and everything it spawns: sort_thread,
+ * msb_64.c:1477-2259).  Same argument meaning:
+ *   keys[n], rids[n]  numa host arrays, 16-byte aligned (msb_64.c:2272-2275), each with
+ *                     room for size[n] * fudge pairs (msb_64.c:1574-1578);
+ *   size[n]           pairs held by node n on entry; on return the pairs node n
+ *                     holds after the global sort (msb_64.c:2180): node n gets the
+ *                     n-th contiguous key range, ascending, and
+ *                     keys[n][size[n]-1] <= keys[n+1][0];
+ *   threads           accepted for compatibility (the reference asserts 64,
+ *                     msb_64.c:2266); not used, the GPU picks its own grid;
+ *   numa              number of arrays (1..64);
+ *   fudge             capacity factor of every array, >= 1.0;
+ *   description/times NULL, or arrays of >= 16 entries that receive a
+ *                     NULL-terminated list of phase names and their times in
+ *                     microseconds (the reference fills 10 entries,
+ *                     msb_64.c:2391-2401; the phases named here are this
+ *                     implementation's own).
+ * Where the reference picks the node boundaries from a random sample with an
+ * uninitialised seed (thread_data_t.seed is never written), this library uses
+ * the exact numa-quantiles of the sorted keys and, like the reference, never
+ * separates equal keys across a node boundary (msb_64.c:1596-1606).
+ * The order of rids among equal keys is unspecified (MSD radix sort is not
+ * stable; the same holds for the reference).
+ * Aborts (like the reference's asserts) on: misaligned arrays, a node that would
+ * overflow size[n]*fudge, more than MSB64_MAX_PAIRS pairs, or a CUDA error.  */
+void sort(uint64_t **keys, uint64_t **rids, uint64_t *size,
+	  int threads, int numa, double fudge,
+	  char **description, uint64_t *times);
+
+/* mamalloc(): replaces msb_64.c:111-115.  64-byte aligned host memory, released
+ * with free() exactly like the reference's. */
+void *mamalloc(size_t size);
+
+/* ------------------------------------------------------ 2. explicit-error API */
+
+#define MSB64_OK            0
+#define MSB64_ERR_CUDA     -1	/* no device / CUDA runtime error (see msb64_b200_last_error) */
+#define MSB64_ERR_ARG      -2	/* NULL or misaligned pointer, bad numa, fudge < 1 */
+#define MSB64_ERR_TOO_BIG  -3	/* more than MSB64_MAX_PAIRS pairs in one call */
+#define MSB64_ERR_CAPACITY -4	/* a node would exceed size[n] * fudge */
+#define MSB64_ERR_NOMEM    -5	/* device or workspace memory exhausted */
+#define MSB64_ERR_INTERNAL -6	/* device-side work list overflow (a bug) */
+
+/* Largest number of pairs one call sorts on one GPU (32-bit element indices). */
+#define MSB64_MAX_PAIRS 0xFFFF0000ull
+
+#define MSB64_MAX_PHASES 16
+
+/* Same as sort() but returns an error code instead of aborting. */
+int msb64_b200_sort(uint64_t **keys, uint64_t **rids, uint64_t *size,
+		    int threads, int numa, double fudge,
+		    char **description, uint64_t *times);
+
+/* One host array pair, in place (the numa == 1 case of sort()). */
+int msb64_b200_sort_host(uint64_t *keys, uint64_t *rids, uint64_t n);
+
+/* Device-resident sort.  d_keys / d_rids: device pointers to n pairs, sorted in
+ * place (the result always lands in these arrays).  workspace: device memory of
+ * at least msb64_b200_workspace_bytes(n) bytes, 256-byte aligned, or NULL to let
+ * the library allocate and cache one.  stream: a cudaStream_t passed as void*
+ * (NULL = the default stream); the call only enqueues work and does not
+ * synchronise, unless phase_us != NULL, in which case it synchronises and fills
+ * phase_us[0..MSB64_PHASE_COUNT) with device times in microseconds.
+ * This is local_radixsort's role (msb_64.c:1007-1035) for the whole array. */
+size_t msb64_b200_workspace_bytes(uint64_t n);
+int msb64_b200_sort_device(uint64_t *d_keys, uint64_t *d_rids, uint64_t n,
+			   void *workspace, size_t workspace_bytes,
+			   void *stream, uint64_t *phase_us);
+
+/* Phases reported by msb64_b200_sort_device (indices into phase_us). */
+#define MSB64_PHASE_HISTOGRAM 0	/* per-digit histogram kernels        (msb_64.c:701-738)  */
+#define MSB64_PHASE_PLAN      1	/* bucket scans / work lists          (msb_64.c:1020-1034) */
+#define MSB64_PHASE_SCATTER   2	/* partition kernels                  (msb_64.c:740-978)  */
+#define MSB64_PHASE_LOCAL     3	/* small-bucket finish in shared mem  (msb_64.c:126-149, 980-1005) */
+#define MSB64_PHASE_COPY      4	/* buckets finished in the scratch buffer copied home */
+#define MSB64_PHASE_COUNT     5
+
+/* Digit schedule: widths of the MSD digits, most significant first, summing to
+ * 64 (the role of schedule_passes, msb_64.c:1334-1400).  Returns the number of
+ * levels written to bits[] (<= 16).  msb64_b200_set_schedule overrides the
+ * default choice for later calls (count = 0 restores the default). */
+int msb64_b200_get_schedule(uint64_t n, int *bits);
+int msb64_b200_set_schedule(const int *bits, int count);
+
+/* Tuning / introspection. */
+int msb64_b200_device_count(void);
+const char *msb64_b200_last_error(void);
+/* Number of kernels launched by this library since load (for bench.py). */
+uint64_t msb64_b200_launch_count(void);
+/* Statistics of the last msb64_b200_sort_device call, read back from the device
+ * (synchronises the stream): out[0..8) = segments per level 0..7 ... see DESIGN.md.
+ * Returns the number of values written. */
+int msb64_b200_last_stats(uint64_t *out, int cap);
+
+/* --------------------------------------------------------------- 3. helpers */
+
+/* Page-locked host memory for fast host<->device copies (free with
+ * msb64_b200_host_free, NOT free()). */
+void *msb64_b200_host_alloc(size_t bytes);
+void msb64_b200_host_free(void *p);
+
+/* Device memory (so that non-CUDA callers can use the device API over the C ABI). */
+void *msb64_b200_device_alloc(size_t bytes);
+void msb64_b200_device_free(void *p);
+int msb64_b200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int msb64_b200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int msb64_b200_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int msb64_b200_stream_sync(void *stream);
+
+/* Synthetic inputs generated on the device (counter-based splitmix64; NOT the
+ * reference's MT19937-64 of rand.c, which is sequential):
+ *   kind 0: uniform 64-bit keys            kind 1: keys & mask (mask = param)
+ *   kind 2: `param` distinct values        kind 3: ascending   kind 4: descending
+ * rids = element index when d_rids != NULL. */
+int msb64_b200_fill(uint64_t *d_keys, uint64_t *d_rids, uint64_t n,
+		    int kind, uint64_t seed, uint64_t param, void *stream);
+
+/* Device form of check() (msb_64.c:2432-2505): returns in out[0] the number of
+ * descents keys[i] > keys[i+1], out[1] the wrapping sum of keys (the reference's
+ * checksum), out[2] an order-independent digest of the (key, rid) multiset.
+ * Synchronises the stream. */
+int msb64_b200_check(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
+		     uint64_t *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,650 @@
+// msb64_b200.cu -- C ABI (include/msb64_b200.h) and host-side driver of the B200 MSD radix
+// sort.  Compiled for sm_100a only; there is no CPU path in this file or behind it.
+//
+// Host flow of one device sort (msb64_b200_sort_device), all on one stream, no host
+// synchronisation between kernels:
+//
+//   init                               control block, level-0 segment / tiles
+//   for each digit (level) of the schedule:
+//       histogram -> plan -> scatter   (kernels return at once when the level is empty)
+//   local_sort                         all small-bucket units of all levels
+//   copy                               finished buckets that ended in the scratch buffer
+//
+// Reference map: sort() msb_64.c:2261-2430, local_radixsort msb_64.c:1007-1035,
+// schedule_passes msb_64.c:1334-1400, check() msb_64.c:2432-2505.
+#include "../../include/msb64_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "msb64_common.cuh"
+#include "msb64_histogram.cuh"
+#include "msb64_local_sort.cuh"
+#include "msb64_plan.cuh"
+#include "msb64_scatter.cuh"
+
+using namespace msb64;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+std::mutex g_mutex;
+
+int fail(int code, const char *fmt, const char *detail = "")
+{
+	snprintf(g_err, sizeof(g_err), fmt, detail);
+	return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+	do {                                                                               \
+		cudaError_t e_ = (expr);                                                   \
+		if (e_ != cudaSuccess) {                                                   \
+			snprintf(g_err, sizeof(g_err), "%s:%d %s: %s", __FILE__, __LINE__, \
+				 #expr, cudaGetErrorString(e_));                           \
+			return e_ == cudaErrorMemoryAllocation ? MSB64_ERR_NOMEM           \
+							       : MSB64_ERR_CUDA;           \
+		}                                                                          \
+	} while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ schedule
+std::vector<int> g_schedule_override;
+
+// Digit widths, most significant first (the role of schedule_passes, msb_64.c:1334).
+std::vector<int> make_schedule(uint64_t n)
+{
+	(void) n;
+	if (!g_schedule_override.empty()) return g_schedule_override;
+	return std::vector<int>(8, 8);
+}
+
+// ------------------------------------------------------------------ device state
+struct Device {
+	bool ready = false;
+	int sms = 0;
+	int hist_blocks[MAX_BITS + 1] = {0};      // resident blocks per SM, by digit width
+	int scatter_blocks[MAX_BITS + 1] = {0};
+	int local_blocks = 0;
+	// cached allocations (grow-only)
+	void *ws = nullptr;
+	size_t ws_bytes = 0;
+	uint64_t *dkeys = nullptr, *drids = nullptr;
+	size_t dcap = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[4 * MAX_LEVELS + 16];
+	bool events = false;
+	// last sort
+	Control *last_ctl = nullptr;
+	cudaStream_t last_stream = nullptr;
+} g_dev;
+
+template <int BITS>
+int setup_bits()
+{
+	using H = HistCfg<BITS, 256>;
+	using S = ScatterCfg<BITS, 256>;
+	CUDA_TRY(cudaFuncSetAttribute(histogram_kernel<BITS, 256>,
+				      cudaFuncAttributeMaxDynamicSharedMemorySize, int(H::SMEM)));
+	CUDA_TRY(cudaFuncSetAttribute(scatter_kernel<BITS, 256>,
+				      cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::SMEM)));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+		&g_dev.hist_blocks[BITS], histogram_kernel<BITS, 256>, 256, H::SMEM));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+		&g_dev.scatter_blocks[BITS], scatter_kernel<BITS, 256>, 256, S::SMEM));
+	if (g_dev.hist_blocks[BITS] < 1 || g_dev.scatter_blocks[BITS] < 1)
+		return fail(MSB64_ERR_CUDA, "kernel does not fit on an SM%s");
+	return MSB64_OK;
+}
+
+int device_init()
+{
+	if (g_dev.ready) return MSB64_OK;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(MSB64_ERR_CUDA, "no CUDA device: %s",
+			    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+	int dev = 0;
+	CUDA_TRY(cudaGetDevice(&dev));
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+	if (prop.major < 10)
+		return fail(MSB64_ERR_CUDA, "device %s is not sm_100 class", prop.name);
+	g_dev.sms = prop.multiProcessorCount;
+	int rc;
+	if ((rc = setup_bits<4>()) || (rc = setup_bits<5>()) || (rc = setup_bits<6>()) ||
+	    (rc = setup_bits<7>()) || (rc = setup_bits<8>()) || (rc = setup_bits<9>()) ||
+	    (rc = setup_bits<10>()) || (rc = setup_bits<11>()))
+		return rc;
+	CUDA_TRY(cudaFuncSetAttribute(local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				      int(LOCAL_SMEM)));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_dev.local_blocks, local_sort_kernel,
+							       LOCAL_THREADS, LOCAL_SMEM));
+	if (g_dev.local_blocks < 1) return fail(MSB64_ERR_CUDA, "local sort does not fit on an SM%s");
+	CUDA_TRY(cudaStreamCreateWithFlags(&g_dev.stream, cudaStreamNonBlocking));
+	g_dev.ready = true;
+	return MSB64_OK;
+}
+
+int ensure_events()
+{
+	if (g_dev.events) return MSB64_OK;
+	for (auto &ev : g_dev.ev) CUDA_TRY(cudaEventCreate(&ev));
+	g_dev.events = true;
+	return MSB64_OK;
+}
+
+// ------------------------------------------------------------------ workspace
+struct Layout {
+	size_t keys_b, rids_b, segs[2], tiles[2], hist[2], units, copies, ctl, total;
+	uint32_t max_segs, max_tiles, max_units, max_copies;
+};
+
+Layout make_layout(uint64_t n, const std::vector<int> &sched)
+{
+	Layout L;
+	int maxbits = 4;
+	for (int b : sched) maxbits = b > maxbits ? b : maxbits;
+	const uint64_t levels = sched.size();
+	L.max_segs = uint32_t(n / LOCAL_CAP + 2);
+	L.max_tiles = uint32_t(n / TILE + 2 * uint64_t(L.max_segs) + 2);
+	L.max_units = uint32_t(2 * (n / LOCAL_CAP) + 2 * levels * L.max_segs + 16);
+	L.max_copies = uint32_t(n / COPY_TILE + L.max_segs + 2);
+	size_t at = 0;
+	auto take = [&](size_t bytes) { size_t o = at; at = align_up(at + bytes); return o; };
+	L.keys_b = take(n * 8);
+	L.rids_b = take(n * 8);
+	for (int i = 0; i < 2; ++i) L.segs[i] = take(size_t(L.max_segs) * sizeof(Seg));
+	for (int i = 0; i < 2; ++i) L.tiles[i] = take(size_t(L.max_tiles) * sizeof(Tile));
+	for (int i = 0; i < 2; ++i) L.hist[i] = take((size_t(L.max_segs) << maxbits) * 4);
+	L.units = take(size_t(L.max_units) * sizeof(Unit));
+	L.copies = take(size_t(L.max_copies) * sizeof(CopyTile));
+	L.ctl = take(sizeof(Control));
+	L.total = at;
+	return L;
+}
+
+// ------------------------------------------------------------------ launches
+template <int BITS>
+void launch_level(const Ctx &c, int level, int shift, int next_bits, cudaStream_t st,
+		  cudaEvent_t *ev)
+{
+	using H = HistCfg<BITS, 256>;
+	using S = ScatterCfg<BITS, 256>;
+	if (ev) cudaEventRecord(ev[0], st);
+	histogram_kernel<BITS, 256><<<g_dev.sms * g_dev.hist_blocks[BITS], 256, H::SMEM, st>>>(c, level, shift);
+	if (ev) cudaEventRecord(ev[1], st);
+	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits);
+	if (ev) cudaEventRecord(ev[2], st);
+	scatter_kernel<BITS, 256><<<g_dev.sms * g_dev.scatter_blocks[BITS], 256, S::SMEM, st>>>(c, level, shift);
+	if (ev) cudaEventRecord(ev[3], st);
+	g_launches += 3;
+}
+
+int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *workspace,
+		       size_t workspace_bytes, cudaStream_t st, uint64_t *phase_us)
+{
+	int rc = device_init();
+	if (rc) return rc;
+	if (n > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
+	if (phase_us) memset(phase_us, 0, MSB64_PHASE_COUNT * sizeof(uint64_t));
+	if (n < 2) return MSB64_OK;
+	if (!d_keys || !d_rids || (uintptr_t(d_keys) & 15) || (uintptr_t(d_rids) & 15))
+		return fail(MSB64_ERR_ARG, "device arrays must be non-NULL and 16-byte aligned%s");
+
+	const std::vector<int> sched = make_schedule(n);
+	const Layout L = make_layout(n, sched);
+	if (!workspace) {
+		if (g_dev.ws_bytes < L.total) {
+			if (g_dev.ws) cudaFree(g_dev.ws);
+			g_dev.ws = nullptr;
+			g_dev.ws_bytes = 0;
+			CUDA_TRY(cudaMalloc(&g_dev.ws, L.total));
+			g_dev.ws_bytes = L.total;
+		}
+		workspace = g_dev.ws;
+	} else if (workspace_bytes < L.total || (uintptr_t(workspace) & 255)) {
+		return fail(MSB64_ERR_NOMEM, "workspace too small or not 256-byte aligned%s");
+	}
+	char *w = static_cast<char *>(workspace);
+	Ctx c;
+	c.keys[0] = d_keys;
+	c.rids[0] = d_rids;
+	c.keys[1] = reinterpret_cast<uint64_t *>(w + L.keys_b);
+	c.rids[1] = reinterpret_cast<uint64_t *>(w + L.rids_b);
+	for (int i = 0; i < 2; ++i) {
+		c.segs[i] = reinterpret_cast<Seg *>(w + L.segs[i]);
+		c.tiles[i] = reinterpret_cast<Tile *>(w + L.tiles[i]);
+		c.hist[i] = reinterpret_cast<uint32_t *>(w + L.hist[i]);
+	}
+	c.units = reinterpret_cast<Unit *>(w + L.units);
+	c.copies = reinterpret_cast<CopyTile *>(w + L.copies);
+	c.ctl = reinterpret_cast<Control *>(w + L.ctl);
+	c.n = uint32_t(n);
+	c.max_segs = L.max_segs;
+	c.max_tiles = L.max_tiles;
+	c.max_units = L.max_units;
+	c.max_copies = L.max_copies;
+
+	cudaEvent_t *ev = nullptr;
+	if (phase_us) {
+		if ((rc = ensure_events())) return rc;
+		ev = g_dev.ev;
+	}
+	const int levels = int(sched.size());
+	if (ev) cudaEventRecord(ev[0], st);
+	init_kernel<<<g_dev.sms, 256, 0, st>>>(c, sched[0]);
+	g_launches += 1;
+	if (n > LOCAL_CAP) {
+		int shift = 64;
+		for (int l = 0; l < levels; ++l) {
+			const int bits = sched[l];
+			shift -= bits;
+			const int next_bits = l + 1 < levels ? sched[l + 1] : 0;
+			cudaEvent_t *lev = ev ? ev + 1 + 4 * l : nullptr;
+			switch (bits) {
+			case 4: launch_level<4>(c, l, shift, next_bits, st, lev); break;
+			case 5: launch_level<5>(c, l, shift, next_bits, st, lev); break;
+			case 6: launch_level<6>(c, l, shift, next_bits, st, lev); break;
+			case 7: launch_level<7>(c, l, shift, next_bits, st, lev); break;
+			case 8: launch_level<8>(c, l, shift, next_bits, st, lev); break;
+			case 9: launch_level<9>(c, l, shift, next_bits, st, lev); break;
+			case 10: launch_level<10>(c, l, shift, next_bits, st, lev); break;
+			case 11: launch_level<11>(c, l, shift, next_bits, st, lev); break;
+			default: return fail(MSB64_ERR_ARG, "digit width outside 4..11%s");
+			}
+		}
+	}
+	cudaEvent_t *tail = ev ? ev + 1 + 4 * levels : nullptr;
+	if (tail) cudaEventRecord(tail[0], st);
+	local_sort_kernel<<<g_dev.sms * g_dev.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(c);
+	if (tail) cudaEventRecord(tail[1], st);
+	copy_kernel<<<g_dev.sms * 8, 256, 0, st>>>(c);
+	if (tail) cudaEventRecord(tail[2], st);
+	g_launches += 2;
+	CUDA_TRY(cudaGetLastError());
+	g_dev.last_ctl = c.ctl;
+	g_dev.last_stream = st;
+
+	if (phase_us) {
+		CUDA_TRY(cudaStreamSynchronize(st));
+		auto us = [&](cudaEvent_t a, cudaEvent_t b) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, a, b);
+			return uint64_t(ms * 1000.0f + 0.5f);
+		};
+		phase_us[MSB64_PHASE_PLAN] += us(ev[0], ev[1]);
+		if (n > LOCAL_CAP)
+			for (int l = 0; l < levels; ++l) {
+				cudaEvent_t *lev = ev + 1 + 4 * l;
+				phase_us[MSB64_PHASE_HISTOGRAM] += us(lev[0], lev[1]);
+				phase_us[MSB64_PHASE_PLAN] += us(lev[1], lev[2]);
+				phase_us[MSB64_PHASE_SCATTER] += us(lev[2], lev[3]);
+			}
+		phase_us[MSB64_PHASE_LOCAL] = us(tail[0], tail[1]);
+		phase_us[MSB64_PHASE_COPY] = us(tail[1], tail[2]);
+		Control h;
+		CUDA_TRY(cudaMemcpy(&h, c.ctl, sizeof(h), cudaMemcpyDeviceToHost));
+		if (h.error) return fail(MSB64_ERR_INTERNAL, "device work list overflow%s");
+	}
+	return MSB64_OK;
+}
+
+// ------------------------------------------------------------------ fill / check kernels
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+	x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+	x ^= x >> 27; x *= 0x94d049bb133111ebull;
+	x ^= x >> 31;
+	return x;
+}
+
+__global__ void fill_kernel(uint64_t *keys, uint64_t *rids, uint64_t n, int kind, uint64_t seed,
+			    uint64_t param)
+{
+	for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n;
+	     i += uint64_t(gridDim.x) * blockDim.x) {
+		const uint64_t x = mix64(seed * 0x9e3779b97f4a7c15ull + i + 1);
+		uint64_t k;
+		switch (kind) {
+		case 1: k = x & param; break;
+		case 2: k = mix64((x % (param ? param : 1)) + 0x51ed27ull); break;
+		case 3: k = i * (param ? param : 1); break;
+		case 4: k = (n - 1 - i) * (param ? param : 1); break;
+		default: k = x;
+		}
+		keys[i] = k;
+		if (rids) rids[i] = i;
+	}
+}
+
+// descents, wrapping key sum, order-independent (key, rid) digest -- the device form of
+// check() (msb_64.c:2432-2505); the digest formula is the oracle's orc_pair_digest.
+__global__ void check_kernel(const uint64_t *keys, const uint64_t *rids, uint64_t n,
+			     unsigned long long *out)
+{
+	unsigned long long bad = 0, sum = 0, dig = 0;
+	for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n;
+	     i += uint64_t(gridDim.x) * blockDim.x) {
+		const uint64_t k = keys[i];
+		if (i + 1 < n && k > keys[i + 1]) bad++;
+		sum += k;
+		if (rids) dig += mix64(k + 0x9e3779b97f4a7c15ull * mix64(rids[i] + 1));
+	}
+	for (int d = 16; d; d >>= 1) {
+		bad += __shfl_xor_sync(0xffffffffu, bad, d);
+		sum += __shfl_xor_sync(0xffffffffu, sum, d);
+		dig += __shfl_xor_sync(0xffffffffu, dig, d);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(&out[0], bad);
+		atomicAdd(&out[1], sum);
+		atomicAdd(&out[2], dig);
+	}
+}
+
+// node boundaries of sort(): first index whose key exceeds the key at each quantile
+__global__ void boundary_kernel(const uint64_t *keys, uint64_t n, int numa, uint64_t *bounds)
+{
+	const int node = threadIdx.x;
+	if (node >= numa) return;
+	if (node == numa - 1) {
+		bounds[node] = n;
+		return;
+	}
+	const uint64_t q = (n / numa) * (node + 1);
+	if (q == 0) {
+		bounds[node] = 0;
+		return;
+	}
+	const uint64_t delim = keys[q - 1];
+	uint64_t lo = q, hi = n;              // first index in [q, n) with key > delim
+	while (lo < hi) {
+		const uint64_t mid = (lo + hi) >> 1;
+		if (keys[mid] > delim) hi = mid;
+		else lo = mid + 1;
+	}
+	bounds[node] = lo;
+}
+
+int ensure_device_arrays(uint64_t n)
+{
+	if (g_dev.dcap >= n) return MSB64_OK;
+	if (g_dev.dkeys) cudaFree(g_dev.dkeys);
+	if (g_dev.drids) cudaFree(g_dev.drids);
+	g_dev.dkeys = g_dev.drids = nullptr;
+	g_dev.dcap = 0;
+	CUDA_TRY(cudaMalloc(&g_dev.dkeys, align_up(n * 8)));
+	CUDA_TRY(cudaMalloc(&g_dev.drids, align_up(n * 8)));
+	g_dev.dcap = n;
+	return MSB64_OK;
+}
+
+const char *kPhaseNames[] = {
+	"Copy to device time:      ", "Histogram time:           ", "Plan time:                ",
+	"Scatter time:             ", "Local sort time:          ", "Copy home time:           ",
+	"Copy to host time:        ",
+};
+
+int sort_host_locked(uint64_t **keys, uint64_t **rids, uint64_t *size, int numa, double fudge,
+		     char **description, uint64_t *times)
+{
+	int rc = device_init();
+	if (rc) return rc;
+	if (!keys || !rids || !size || numa < 1 || numa > 64 || !(fudge >= 1.0))
+		return fail(MSB64_ERR_ARG, "bad keys/rids/size/numa/fudge%s");
+	uint64_t total = 0;
+	for (int n = 0; n < numa; ++n) {
+		if (size[n] && (!keys[n] || !rids[n])) return fail(MSB64_ERR_ARG, "NULL array%s");
+		if ((uintptr_t(keys[n]) & 15) || (uintptr_t(rids[n]) & 15))
+			return fail(MSB64_ERR_ARG, "arrays must be 16-byte aligned (msb_64.c:2272)%s");
+		total += size[n];
+	}
+	if (total > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
+	if (description) description[0] = nullptr;
+	if (total == 0) return MSB64_OK;
+	if ((rc = ensure_device_arrays(total))) return rc;
+	if ((rc = ensure_events())) return rc;
+	cudaStream_t st = g_dev.stream;
+	cudaEvent_t *ev = g_dev.ev + (4 * MAX_LEVELS + 8);     // spare events past the per-level ones
+
+	CUDA_TRY(cudaEventRecord(ev[0], st));
+	uint64_t at = 0;
+	for (int n = 0; n < numa; ++n) {
+		if (!size[n]) continue;
+		CUDA_TRY(cudaMemcpyAsync(g_dev.dkeys + at, keys[n], size[n] * 8, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(g_dev.drids + at, rids[n], size[n] * 8, cudaMemcpyHostToDevice, st));
+		at += size[n];
+	}
+	CUDA_TRY(cudaEventRecord(ev[1], st));
+	uint64_t phase[MSB64_PHASE_COUNT];
+	rc = sort_device_locked(g_dev.dkeys, g_dev.drids, total, nullptr, 0, st, times ? phase : nullptr);
+	if (rc) return rc;
+
+	// node boundaries: exact quantiles, equal keys never split (msb_64.c:1596-1606)
+	std::vector<uint64_t> bounds(numa, total);
+	if (numa > 1) {
+		uint64_t *d_bounds = reinterpret_cast<uint64_t *>(g_dev.ws);   // B keys are dead now
+		boundary_kernel<<<1, 64, 0, st>>>(g_dev.dkeys, total, numa, d_bounds);
+		g_launches += 1;
+		CUDA_TRY(cudaMemcpyAsync(bounds.data(), d_bounds, numa * 8, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		uint64_t prev = 0;
+		for (int n = 0; n < numa; ++n) {
+			const uint64_t cap = uint64_t(double(size[n]) * fudge);     // msb_64.c:1574
+			if (bounds[n] - prev > cap)
+				return fail(MSB64_ERR_CAPACITY, "a node would exceed size[n] * fudge%s");
+			prev = bounds[n];
+		}
+	}
+	CUDA_TRY(cudaEventRecord(ev[2], st));
+	uint64_t prev = 0;
+	for (int n = 0; n < numa; ++n) {
+		const uint64_t cnt = bounds[n] - prev;
+		if (cnt) {
+			CUDA_TRY(cudaMemcpyAsync(keys[n], g_dev.dkeys + prev, cnt * 8, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(rids[n], g_dev.drids + prev, cnt * 8, cudaMemcpyDeviceToHost, st));
+		}
+		size[n] = cnt;
+		prev = bounds[n];
+	}
+	CUDA_TRY(cudaEventRecord(ev[3], st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	if (total >= 2) {
+		Control h;
+		CUDA_TRY(cudaMemcpy(&h, g_dev.last_ctl, sizeof(h), cudaMemcpyDeviceToHost));
+		if (h.error) return fail(MSB64_ERR_INTERNAL, "device work list overflow%s");
+	}
+	if (times && description) {
+		float h2d = 0, d2h = 0;
+		cudaEventElapsedTime(&h2d, ev[0], ev[1]);
+		cudaEventElapsedTime(&d2h, ev[2], ev[3]);
+		times[0] = uint64_t(h2d * 1000);
+		for (int p = 0; p < MSB64_PHASE_COUNT; ++p) times[1 + p] = phase[p];
+		times[1 + MSB64_PHASE_COUNT] = uint64_t(d2h * 1000);
+		for (int p = 0; p < 2 + MSB64_PHASE_COUNT; ++p) description[p] = const_cast<char *>(kPhaseNames[p]);
+		description[2 + MSB64_PHASE_COUNT] = nullptr;
+	}
+	return MSB64_OK;
+}
+
+} // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+int msb64_b200_sort(uint64_t **keys, uint64_t **rids, uint64_t *size, int threads, int numa,
+		    double fudge, char **description, uint64_t *times)
+{
+	(void) threads;
+	std::lock_guard<std::mutex> lock(g_mutex);
+	return sort_host_locked(keys, rids, size, numa, fudge, description, times);
+}
+
+void sort(uint64_t **keys, uint64_t **rids, uint64_t *size, int threads, int numa, double fudge,
+	  char **description, uint64_t *times)
+{
+	const int rc = msb64_b200_sort(keys, rids, size, threads, numa, fudge, description, times);
+	if (rc != MSB64_OK) {
+		fprintf(stderr, "msb64_b200 sort(): error %d: %s\n", rc, g_err);
+		abort();
+	}
+}
+
+void *mamalloc(size_t size)
+{
+	void *ptr = nullptr;
+	return posix_memalign(&ptr, 64, size) ? nullptr : ptr;
+}
+
+int msb64_b200_sort_host(uint64_t *keys, uint64_t *rids, uint64_t n)
+{
+	uint64_t *k[1] = {keys}, *r[1] = {rids}, s[1] = {n};
+	return msb64_b200_sort(k, r, s, 64, 1, 1.0, nullptr, nullptr);
+}
+
+size_t msb64_b200_workspace_bytes(uint64_t n)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	return make_layout(n, make_schedule(n)).total;
+}
+
+int msb64_b200_sort_device(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *workspace,
+			   size_t workspace_bytes, void *stream, uint64_t *phase_us)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	return sort_device_locked(d_keys, d_rids, n, workspace, workspace_bytes,
+				  static_cast<cudaStream_t>(stream), phase_us);
+}
+
+int msb64_b200_get_schedule(uint64_t n, int *bits)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	const std::vector<int> s = make_schedule(n);
+	for (size_t i = 0; i < s.size(); ++i) bits[i] = s[i];
+	return int(s.size());
+}
+
+int msb64_b200_set_schedule(const int *bits, int count)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	if (count == 0) {
+		g_schedule_override.clear();
+		return MSB64_OK;
+	}
+	if (count < 0 || count > MAX_LEVELS || !bits) return fail(MSB64_ERR_ARG, "bad schedule%s");
+	int sum = 0;
+	for (int i = 0; i < count; ++i) {
+		if (bits[i] < 4 || bits[i] > MAX_BITS) return fail(MSB64_ERR_ARG, "digit width outside 4..11%s");
+		sum += bits[i];
+	}
+	if (sum != 64) return fail(MSB64_ERR_ARG, "digit widths must sum to 64%s");
+	g_schedule_override.assign(bits, bits + count);
+	return MSB64_OK;
+}
+
+int msb64_b200_device_count(void)
+{
+	int count = 0;
+	return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0;
+}
+
+const char *msb64_b200_last_error(void) { return g_err; }
+
+uint64_t msb64_b200_launch_count(void) { return g_launches.load(); }
+
+int msb64_b200_last_stats(uint64_t *out, int cap)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	if (!g_dev.last_ctl) return 0;
+	if (cudaStreamSynchronize(g_dev.last_stream) != cudaSuccess) return 0;
+	Control h;
+	if (cudaMemcpy(&h, g_dev.last_ctl, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+	int k = 0;
+	for (int l = 0; l < MAX_LEVELS && k < cap; ++l) out[k++] = h.nsegs[l];
+	for (int l = 0; l < MAX_LEVELS && k < cap; ++l) out[k++] = h.ntiles[l];
+	if (k < cap) out[k++] = h.nunits;
+	if (k < cap) out[k++] = h.ncopies;
+	if (k < cap) out[k++] = h.error;
+	if (k < cap) out[k++] = h.degenerate;
+	return k;
+}
+
+void *msb64_b200_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void msb64_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void *msb64_b200_device_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+void msb64_b200_device_free(void *p) { if (p) cudaFree(p); }
+
+int msb64_b200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+	return MSB64_OK;
+}
+int msb64_b200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
+{
+	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+	return MSB64_OK;
+}
+int msb64_b200_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+	return MSB64_OK;
+}
+int msb64_b200_stream_sync(void *stream)
+{
+	CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+	return MSB64_OK;
+}
+
+int msb64_b200_fill(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, int kind, uint64_t seed,
+		    uint64_t param, void *stream)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	int rc = device_init();
+	if (rc) return rc;
+	if (!n) return MSB64_OK;
+	fill_kernel<<<g_dev.sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_keys, d_rids, n, kind,
+										seed, param);
+	g_launches += 1;
+	CUDA_TRY(cudaGetLastError());
+	return MSB64_OK;
+}
+
+int msb64_b200_check(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, uint64_t *out,
+		     void *stream)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	int rc = device_init();
+	if (rc) return rc;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	unsigned long long *d_out = nullptr;
+	CUDA_TRY(cudaMalloc(&d_out, 3 * sizeof(unsigned long long)));
+	CUDA_TRY(cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), st));
+	if (n) {
+		check_kernel<<<g_dev.sms * 8, 256, 0, st>>>(d_keys, d_rids, n, d_out);
+		g_launches += 1;
+	}
+	cudaError_t e = cudaMemcpyAsync(out, d_out, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	cudaFree(d_out);
+	CUDA_TRY(e);
+	return MSB64_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,160 @@
+// msb64_common.cuh -- device-side data model shared by the msb64 kernels (sm_100a only).
+//
+// The sort is an MSD radix sort over 64-bit keys with 64-bit rids riding along
+// (reference: local_radixsort, msb_64.c:1007-1035).  One "level" consumes one
+// digit.  The state between kernels lives in HBM:
+//
+//   buffers   A = the caller's arrays (buf 0), B = scratch of the same size (buf 1)
+//   Seg       a bucket still too large for shared memory: [begin, begin+size) in
+//             buffer `buf`; it is histogrammed and scattered at the next level
+//   Tile      TILE consecutive element slots of one Seg; the unit of work of the
+//             histogram and scatter kernels
+//   Unit      a run of neighbouring small buckets (<= LOCAL_CAP pairs together)
+//             finished by the local sort kernel entirely in shared memory
+//   CopyTile  a piece of a finished bucket that ended in B and is copied to A
+//
+// Every list is filled by the plan kernel of the level above through atomic
+// counters in Control; no kernel waits on another block.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msb64 {
+
+constexpr int MAX_LEVELS = 16;          // digits per key (64 bits / >= 4 bits)
+constexpr int MAX_BITS = 11;            // widest digit a level may use
+constexpr uint32_t LOCAL_CAP = 4096;    // pairs the local sort holds in shared memory
+constexpr uint32_t TILE = 4096;         // element slots per histogram/scatter tile
+constexpr uint32_t COPY_TILE = 8192;    // pairs per copy tile
+
+struct Seg {
+	uint32_t begin;   // first element
+	uint32_t size;    // > LOCAL_CAP by construction
+	uint32_t buf;     // buffer holding it now (0 = A, 1 = B)
+	uint32_t skip;    // set by plan: every key has the same digit, nothing to move
+};
+
+struct Tile {
+	uint32_t seg;     // index into this level's Seg list
+	uint32_t idx;     // tile number inside the Seg
+};
+
+struct Unit {
+	uint32_t begin;
+	uint32_t size;    // 1..LOCAL_CAP
+	uint32_t buf;     // where the pairs are now; they are always written to A
+	uint32_t pad;
+};
+
+struct CopyTile {
+	uint32_t begin;
+	uint32_t size;    // 1..COPY_TILE, B -> A
+};
+
+struct Control {
+	uint32_t nsegs[MAX_LEVELS + 1];
+	uint32_t ntiles[MAX_LEVELS + 1];
+	uint32_t nunits;
+	uint32_t ncopies;
+	uint32_t error;          // bit 0: Seg list overflow, 1: Tile, 2: Unit, 3: CopyTile
+	uint32_t degenerate;     // segments whose scatter was skipped (statistics)
+};
+
+// Everything a kernel needs, passed by value.
+struct Ctx {
+	uint64_t *keys[2];
+	uint64_t *rids[2];
+	Seg *segs[2];            // ping-pong by level parity
+	Tile *tiles[2];
+	uint32_t *hist[2];       // [seg][bin] counts, turned into write cursors by plan
+	Unit *units;
+	CopyTile *copies;
+	Control *ctl;
+	uint32_t n;
+	uint32_t max_segs, max_tiles, max_units, max_copies;
+};
+
+// Tiles of a Seg start at an even element so that 16-byte loads stay aligned.
+__host__ __device__ inline uint32_t seg_tile_origin(uint32_t begin) { return begin & ~1u; }
+__host__ __device__ inline uint32_t seg_tile_count(uint32_t begin, uint32_t size)
+{
+	return (begin + size - seg_tile_origin(begin) + TILE - 1) / TILE;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+	uint32_t m;
+	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+	return m;
+}
+
+// Lanes of the warp whose `digit` equals mine (warp-level multisplit by ballots:
+// one vote per digit bit; no shared-memory atomics on the hot path).
+template <int BITS>
+__device__ __forceinline__ uint32_t match_digit(uint32_t digit)
+{
+	uint32_t peers = 0xffffffffu;
+#pragma unroll
+	for (int b = 0; b < BITS; ++b) {
+		const bool bit = (digit >> b) & 1u;
+		const uint32_t votes = __ballot_sync(0xffffffffu, bit);
+		peers &= bit ? votes : ~votes;
+	}
+	return peers;
+}
+
+// Streaming 16-byte / 8-byte global accesses: the sort touches every byte once per
+// pass, so nothing is worth keeping in L1.
+__device__ __forceinline__ ulonglong2 ld_stream_u64x2(const uint64_t *p)
+{
+	ulonglong2 v;
+	asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
+		     : "=l"(v.x), "=l"(v.y) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p)
+{
+	uint64_t v;
+	asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void st_stream_u64(uint64_t *p, uint64_t v)
+{
+	asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Inclusive-to-exclusive block scan helper over one value per thread.
+// scratch: THREADS/32 + 1 words of shared memory.  Returns the exclusive prefix;
+// *total receives the block sum.  Contains two __syncthreads().
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *scratch,
+							 uint32_t *total)
+{
+	constexpr int WARPS = THREADS / 32;
+	const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d) inc += t;
+	}
+	if (lane == 31) scratch[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = lane < WARPS ? scratch[lane] : 0;
+		uint32_t winc = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+			if (lane >= d) winc += t;
+		}
+		if (lane < WARPS) scratch[lane] = winc - w;
+		if (lane == 31) scratch[WARPS] = winc;
+	}
+	__syncthreads();
+	*total = scratch[WARPS];
+	return inc - v + scratch[warp];
+}
+
+} // namespace msb64

@@ -1,0 +1,143 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Oracle = oracle/msb64_oracle.c (restated msb_64.c).  Keys must match the oracle's
+sorted key sequence exactly; rids must carry the same (key, rid) multiset (MSD radix
+sort is not stable, neither here nor in the reference), which is checked exactly at
+these sizes: sorting rids inside every run of equal keys on both sides and comparing.
+"""
+import numpy as np
+import pytest
+
+from inputs import KINDS, make
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 2, 3, 17, 255, 256, 257, 4095, 4096, 4097, 8191, 8193, 12289, 65536 + 3,
+         300_001, 1 << 20]
+
+
+def canon(keys, rids):
+    """Order rids inside equal-key runs so that two correct outputs compare equal."""
+    order = np.lexsort((rids, keys))
+    return keys[order], rids[order]
+
+
+def oracle_sorted(oracle, keys, rids):
+    k, r = keys.copy(), rids.copy()
+    if k.size:
+        # whole sort of the reference: sample, 128 ranges, local MSB radix sort per range
+        pad_k = np.concatenate([k, np.zeros(k.size // 2 + 64, dtype=np.uint64)])
+        pad_r = np.concatenate([r, np.zeros(k.size // 2 + 64, dtype=np.uint64)])
+        oracle.sort([pad_k], [pad_r], [k.size])
+        k, r = pad_k[:k.size].copy(), pad_r[:k.size].copy()
+    return k, r
+
+
+def run_case(gpu, oracle, keys, rids):
+    n = keys.size
+    gk, gr = keys.copy(), rids.copy()
+    gpu.sort_pairs(gk, gr)
+    ok, orr = oracle_sorted(oracle, keys, rids)
+    assert np.array_equal(gk, ok), "keys differ from the oracle's sorted keys"
+    ck, cr = canon(gk, gr)
+    ek, er = canon(ok, orr)
+    assert np.array_equal(cr, er), "(key, rid) multiset differs from the oracle's"
+    assert n == 0 or np.all(gk[:-1] <= gk[1:])
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_uniform_sizes(gpu, oracle, n):
+    keys = make("uniform", n, seed=n + 1)
+    run_case(gpu, oracle, keys, np.arange(n, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n", [5000, 100_003, 1 << 19])
+def test_distributions(gpu, oracle, kind, n):
+    keys = make(kind, n, seed=7)
+    rids = np.arange(n, dtype=np.uint64) * np.uint64(3) + np.uint64(11)
+    run_case(gpu, oracle, keys, rids)
+
+
+@pytest.mark.parametrize("sched", [[8] * 8, [4] * 16, [11, 11, 11, 11, 11, 9], [10, 10, 8, 8, 8, 8, 8, 4],
+                                   [9, 9, 9, 9, 9, 9, 10], [5, 6, 7, 8, 9, 10, 11, 8]])
+@pytest.mark.parametrize("kind", ["uniform", "dup1000", "low24", "skew", "clustered"])
+def test_schedules(gpu, oracle, sched, kind):
+    n = 250_007
+    keys = make(kind, n, seed=3)
+    gpu.set_schedule(sched)
+    try:
+        assert gpu.get_schedule(n) == sched
+        run_case(gpu, oracle, keys, np.arange(n, dtype=np.uint64))
+    finally:
+        gpu.set_schedule(None)
+
+
+def test_keys_equal_rids_reference_check(gpu):
+    """The reference benchmark's own acceptance test: rids = keys, then check(..., same=1)
+    (msb_64.c:2470): ascending keys, key == rid everywhere, checksum = sum of keys."""
+    n = 1 << 21
+    keys = make("uniform", n, seed=99)
+    rids = keys.copy()
+    expect = int(np.sum(keys, dtype=np.uint64))
+    size = [n]
+    gpu.sort([keys], [rids], size)
+    assert size == [n]
+    assert gpu.check([keys], [rids], size, same=True) == expect
+
+
+def test_numa_nodes(gpu, oracle):
+    """sort() over several arrays: node n gets the n-th key range, equal keys are never
+    split, sizes are updated (msb_64.c:2180, 1596-1606)."""
+    numa, per = 4, 200_000
+    fudge = 1.5
+    rng = np.random.default_rng(5)
+    keys = [np.concatenate([make("dup1000", per, seed=10 + i), np.zeros(per, dtype=np.uint64)])
+            for i in range(numa)]
+    rids = [np.concatenate([rng.integers(0, 1 << 64, size=per, dtype=np.uint64),
+                            np.zeros(per, dtype=np.uint64)]) for i in range(numa)]
+    all_k = np.concatenate([k[:per] for k in keys])
+    all_r = np.concatenate([r[:per] for r in rids])
+    size = [per] * numa
+    gpu.sort(keys, rids, size, numa=numa, fudge=fudge)
+    assert sum(size) == numa * per
+    out_k = np.concatenate([keys[i][:size[i]] for i in range(numa)])
+    out_r = np.concatenate([rids[i][:size[i]] for i in range(numa)])
+    assert np.array_equal(out_k, np.sort(all_k))
+    ck, cr = canon(out_k, out_r)
+    ek, er = canon(all_k, all_r)
+    assert np.array_equal(cr, er)
+    for i in range(numa - 1):
+        if size[i] and size[i + 1]:
+            assert keys[i][size[i] - 1] < keys[i + 1][0], "equal keys split across nodes"
+    gpu.check(keys, rids, size, numa=numa)
+
+
+def test_capacity_error(gpu):
+    """All-equal keys cannot be spread over two nodes: the reference asserts, we report."""
+    per = 10_000
+    keys = [np.zeros(per, dtype=np.uint64) for _ in range(2)]
+    rids = [np.zeros(per, dtype=np.uint64) for _ in range(2)]
+    with pytest.raises(gpu.Msb64Error) as e:
+        gpu.sort(keys, rids, [per, per], numa=2, fudge=1.0)
+    assert e.value.code == -4
+
+
+def test_device_resident_and_digest(gpu, oracle):
+    """Device API + device-side check: sortedness, checksum and the order-independent
+    (key, rid) digest equal the oracle's on the same input."""
+    n = (1 << 22) + 12345
+    with gpu.DeviceArray(n) as dk, gpu.DeviceArray(n) as dr:
+        gpu.fill(dk, dr, kind=0, seed=42)
+        keys, rids = dk.download(), dr.download()
+        before = oracle.pair_digest(keys, rids)
+        phases = gpu.sort_device(dk.ptr, dr.ptr, n, timed=True)
+        assert set(phases) == {"histogram", "plan", "scatter", "local_sort", "copy_home"}
+        bad, csum, digest = dk.check(dr)
+        assert bad == 0
+        assert digest == before
+        assert csum == int(np.sum(keys, dtype=np.uint64))
+        out = dk.download()
+        assert np.array_equal(out, np.sort(keys))
+        stats = gpu.last_stats()
+        assert stats["error"] == 0
