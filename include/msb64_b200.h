@@ -123,6 +123,11 @@ uint64_t msb64_b200_launch_count(void);
  * Returns the number of values written. */
 int msb64_b200_last_stats(uint64_t *out, int cap);
 
+/* Per-level device times of the last msb64_b200_sort_device call that passed
+ * phase_us: out[3*l + 0..2] = histogram, plan, scatter microseconds of level l.
+ * Returns the number of values written (3 * levels). */
+int msb64_b200_last_level_times(uint64_t *out, int cap);
+
 /* --------------------------------------------------------------- 3. helpers */
 
 /* Page-locked host memory for fast host<->device copies (free with

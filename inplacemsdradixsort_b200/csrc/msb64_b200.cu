@@ -81,6 +81,8 @@ struct Device {
 	cudaEvent_t ev[4 * MAX_LEVELS + 16];
 	bool events = false;
 	// last sort
+	uint64_t level_us[MAX_LEVELS][3] = {{0}};   // histogram, plan, scatter per level (timed sorts)
+	int last_levels = 0;
 	Control *last_ctl = nullptr;
 	cudaStream_t last_stream = nullptr;
 } g_dev;
@@ -284,10 +286,14 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 		if (n > LOCAL_CAP)
 			for (int l = 0; l < levels; ++l) {
 				cudaEvent_t *lev = ev + 1 + 4 * l;
-				phase_us[MSB64_PHASE_HISTOGRAM] += us(lev[0], lev[1]);
-				phase_us[MSB64_PHASE_PLAN] += us(lev[1], lev[2]);
-				phase_us[MSB64_PHASE_SCATTER] += us(lev[2], lev[3]);
+				g_dev.level_us[l][0] = us(lev[0], lev[1]);
+				g_dev.level_us[l][1] = us(lev[1], lev[2]);
+				g_dev.level_us[l][2] = us(lev[2], lev[3]);
+				phase_us[MSB64_PHASE_HISTOGRAM] += g_dev.level_us[l][0];
+				phase_us[MSB64_PHASE_PLAN] += g_dev.level_us[l][1];
+				phase_us[MSB64_PHASE_SCATTER] += g_dev.level_us[l][2];
 			}
+		g_dev.last_levels = n > LOCAL_CAP ? levels : 0;
 		phase_us[MSB64_PHASE_LOCAL] = us(tail[0], tail[1]);
 		phase_us[MSB64_PHASE_COPY] = us(tail[1], tail[2]);
 		Control h;
@@ -574,6 +580,17 @@ int msb64_b200_last_stats(uint64_t *out, int cap)
 	if (k < cap) out[k++] = h.ncopies;
 	if (k < cap) out[k++] = h.error;
 	if (k < cap) out[k++] = h.degenerate;
+	if (k < cap) out[k++] = h.local_pairs;
+	for (int l = 0; l < MAX_LEVELS && k < cap; ++l) out[k++] = h.moved[l];
+	return k;
+}
+
+int msb64_b200_last_level_times(uint64_t *out, int cap)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	int k = 0;
+	for (int l = 0; l < g_dev.last_levels; ++l)
+		for (int j = 0; j < 3 && k < cap; ++j) out[k++] = g_dev.level_us[l][j];
 	return k;
 }
 

@@ -58,6 +58,8 @@ struct Control {
 	uint32_t ncopies;
 	uint32_t error;          // bit 0: Seg list overflow, 1: Tile, 2: Unit, 3: CopyTile
 	uint32_t degenerate;     // segments whose scatter was skipped (statistics)
+	uint32_t moved[MAX_LEVELS];   // pairs the scatter of each level moves (statistics)
+	uint32_t local_pairs;    // pairs finished by the local sort (statistics)
 };
 
 // Everything a kernel needs, passed by value.

@@ -37,6 +37,8 @@ __global__ void init_kernel(const Ctx c, const int bits0)
 		ctl->ncopies = 0;
 		ctl->error = 0;
 		ctl->degenerate = 0;
+		ctl->local_pairs = c.n <= LOCAL_CAP ? c.n : 0;
+		for (int l = 0; l < MAX_LEVELS; ++l) ctl->moved[l] = 0;
 		if (c.n > LOCAL_CAP) {
 			ctl->nsegs[0] = 1;
 			ctl->ntiles[0] = nt;
@@ -116,10 +118,12 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits)
 			if (degenerate) {
 				segs[sg].skip = 1;
 				atomicAdd(&ctl->degenerate, 1u);
+			} else {
+				atomicAdd(&ctl->moved[level], s.size);
 			}
 			if (!last) {
 				// greedy merge of neighbouring small buckets into units
-				uint32_t run_beg = 0, run_size = 0;
+				uint32_t run_beg = 0, run_size = 0, local_pairs = 0;
 				for (uint32_t b = 0; b <= NB; ++b) {
 					const uint32_t cb = b < NB ? s_cnt[b] : 0xffffffffu;
 					if (cb == 0) continue;
@@ -128,6 +132,7 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits)
 							const uint32_t u = atomicAdd(&ctl->nunits, 1u);
 							if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, 0u};
 							else atomicOr(&ctl->error, 4u);
+							local_pairs += run_size;
 						}
 						run_size = 0;
 						if (cb > LOCAL_CAP) continue;
@@ -135,6 +140,7 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits)
 					if (run_size == 0) run_beg = s_beg[b];
 					run_size += cb;
 				}
+				if (local_pairs) atomicAdd(&ctl->local_pairs, local_pairs);
 				// reserve segment slots and tiles for the large children
 				uint32_t nt = 0;
 				for (uint32_t i = 0; i < s_nlarge; ++i) {

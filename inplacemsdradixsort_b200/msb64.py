@@ -33,7 +33,8 @@ EXPORTS = (
     "sort", "mamalloc", "msb64_b200_sort", "msb64_b200_sort_host",
     "msb64_b200_workspace_bytes", "msb64_b200_sort_device", "msb64_b200_get_schedule",
     "msb64_b200_set_schedule", "msb64_b200_device_count", "msb64_b200_last_error",
-    "msb64_b200_launch_count", "msb64_b200_last_stats", "msb64_b200_host_alloc",
+    "msb64_b200_launch_count", "msb64_b200_last_stats", "msb64_b200_last_level_times",
+    "msb64_b200_host_alloc",
     "msb64_b200_host_free", "msb64_b200_device_alloc", "msb64_b200_device_free",
     "msb64_b200_memcpy_h2d", "msb64_b200_memcpy_d2h", "msb64_b200_memcpy_d2d",
     "msb64_b200_stream_sync", "msb64_b200_fill", "msb64_b200_check",
@@ -87,6 +88,8 @@ def load_library() -> C.CDLL:
     L.msb64_b200_launch_count.restype = C.c_uint64
     L.msb64_b200_last_stats.restype = C.c_int
     L.msb64_b200_last_stats.argtypes = [_u64p, C.c_int]
+    L.msb64_b200_last_level_times.restype = C.c_int
+    L.msb64_b200_last_level_times.argtypes = [_u64p, C.c_int]
     L.msb64_b200_host_alloc.restype = C.c_void_p
     L.msb64_b200_host_alloc.argtypes = [C.c_size_t]
     L.msb64_b200_host_free.argtypes = [C.c_void_p]
@@ -333,11 +336,19 @@ def set_schedule(bits: list[int] | None) -> None:
         _raise(L.msb64_b200_set_schedule(arr, len(bits)))
 
 
+def last_level_times() -> list[dict]:
+    """Per-level device times (microseconds) of the last timed sort_device call."""
+    out = (C.c_uint64 * 48)()
+    k = load_library().msb64_b200_last_level_times(out, 48)
+    return [{"histogram": int(out[i]), "plan": int(out[i + 1]), "scatter": int(out[i + 2])}
+            for i in range(0, k, 3)]
+
+
 def last_stats() -> dict:
-    out = (C.c_uint64 * 40)()
-    k = load_library().msb64_b200_last_stats(out, 40)
+    out = (C.c_uint64 * 64)()
+    k = load_library().msb64_b200_last_stats(out, 64)
     v = [int(out[i]) for i in range(k)]
-    if k < 36:
+    if k < 53:
         return {}
     return {"segments": v[0:16], "tiles": v[16:32], "units": v[32], "copy_tiles": v[33],
-            "error": v[34], "degenerate": v[35]}
+            "error": v[34], "degenerate": v[35], "local_pairs": v[36], "moved": v[37:53]}
