@@ -29,6 +29,16 @@
 
 using namespace msb64;
 
+// launch shape of the scatter kernel (tuned on B200)
+#ifndef MSB64_SCATTER_THREADS
+#define MSB64_SCATTER_THREADS 256
+#endif
+#ifndef MSB64_SCATTER_MINB
+#define MSB64_SCATTER_MINB 2
+#endif
+constexpr int SCATTER_THREADS = MSB64_SCATTER_THREADS;
+constexpr int SCATTER_MINB = MSB64_SCATTER_MINB;
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -60,9 +70,38 @@ std::vector<int> g_schedule_override;
 // Digit widths, most significant first (the role of schedule_passes, msb_64.c:1334).
 std::vector<int> make_schedule(uint64_t n)
 {
-	(void) n;
 	if (!g_schedule_override.empty()) return g_schedule_override;
-	return std::vector<int>(8, 8);
+	// Uniform keys stop descending once the average bucket fits the local sort with
+	// room to spare (2048 pairs): that takes `need` bits.  The scatter's HBM efficiency
+	// falls with the run length TILE / 2^bits (tools/permcopy.cu: 6.3 TB/s at 256-byte
+	// runs, 3.5 TB/s at 64-byte runs), so the `need` bits are spread over the fewest
+	// passes of at most 8 bits, as evenly as possible, widest first.
+	int log_n = 0;
+	while (log_n < 63 && (1ull << log_n) < n) ++log_n;
+	const int need = log_n > 11 ? log_n - 11 : 0;
+	std::vector<int> s;
+	int used = 0;
+	if (need >= 4) {
+		const int passes = (need + 7) / 8;
+		for (int p = 0; p < passes; ++p) {
+			int b = (need - used + (passes - p) - 1) / (passes - p);     // ceil of the even share
+			b = b < 4 ? 4 : b;
+			s.push_back(b);
+			used += b;
+		}
+	}
+	// the rest of the key (only skewed inputs get here): 8-bit digits, widths 4..11 at the end
+	int rest = 64 - used;
+	while (rest >= 16 || rest == 8) {
+		s.push_back(8);
+		rest -= 8;
+	}
+	if (rest > 11) {
+		s.push_back(rest - rest / 2);
+		rest /= 2;
+	}
+	if (rest) s.push_back(rest);
+	return s;
 }
 
 // ------------------------------------------------------------------ device state
@@ -91,15 +130,15 @@ template <int BITS>
 int setup_bits()
 {
 	using H = HistCfg<BITS, 256>;
-	using S = ScatterCfg<BITS, 256>;
+	using S = ScatterCfg<BITS, SCATTER_THREADS>;
 	CUDA_TRY(cudaFuncSetAttribute(histogram_kernel<BITS, 256>,
 				      cudaFuncAttributeMaxDynamicSharedMemorySize, int(H::SMEM)));
-	CUDA_TRY(cudaFuncSetAttribute(scatter_kernel<BITS, 256>,
+	CUDA_TRY(cudaFuncSetAttribute(scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB>,
 				      cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::SMEM)));
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
 		&g_dev.hist_blocks[BITS], histogram_kernel<BITS, 256>, 256, H::SMEM));
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-		&g_dev.scatter_blocks[BITS], scatter_kernel<BITS, 256>, 256, S::SMEM));
+		&g_dev.scatter_blocks[BITS], scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB>, SCATTER_THREADS, S::SMEM));
 	if (g_dev.hist_blocks[BITS] < 1 || g_dev.scatter_blocks[BITS] < 1)
 		return fail(MSB64_ERR_CUDA, "kernel does not fit on an SM%s");
 	return MSB64_OK;
@@ -179,13 +218,13 @@ void launch_level(const Ctx &c, int level, int shift, int next_bits, cudaStream_
 		  cudaEvent_t *ev)
 {
 	using H = HistCfg<BITS, 256>;
-	using S = ScatterCfg<BITS, 256>;
+	using S = ScatterCfg<BITS, SCATTER_THREADS>;
 	if (ev) cudaEventRecord(ev[0], st);
 	histogram_kernel<BITS, 256><<<g_dev.sms * g_dev.hist_blocks[BITS], 256, H::SMEM, st>>>(c, level, shift);
 	if (ev) cudaEventRecord(ev[1], st);
 	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits);
 	if (ev) cudaEventRecord(ev[2], st);
-	scatter_kernel<BITS, 256><<<g_dev.sms * g_dev.scatter_blocks[BITS], 256, S::SMEM, st>>>(c, level, shift);
+	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<g_dev.sms * g_dev.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, shift);
 	if (ev) cudaEventRecord(ev[3], st);
 	g_launches += 3;
 }

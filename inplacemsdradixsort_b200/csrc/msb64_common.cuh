@@ -123,7 +123,13 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p)
 }
 __device__ __forceinline__ void st_stream_u64(uint64_t *p, uint64_t v)
 {
+#if defined(MSB64_PLAIN_STORES)
+	*p = v;
+#elif defined(MSB64_CS_STORES)
+	__stcs(reinterpret_cast<unsigned long long *>(p), v);
+#else
 	asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+#endif
 }
 
 // Inclusive-to-exclusive block scan helper over one value per thread.

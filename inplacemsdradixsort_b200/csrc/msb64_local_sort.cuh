@@ -6,13 +6,16 @@
 // on some prefix and may differ anywhere below; the block
 //   1. loads keys and rids (coalesced) and ORs together key ^ first_key: the set bits
 //      are exactly the bit positions in which the unit's keys differ;
-//   2. counting-sorts the pairs in shared memory on the top `b` differing bits
-//      (b <= LOCAL_BITS): histogram, block scan, placement;
-//   3. finishes every bin that still holds different keys: short bins by a serial
-//      insertion sort of one thread (msb_64.c:126-149 does the same below 20 items),
-//      long bins by a block-wide bitonic network (the fallback for adversarial bit
-//      patterns; random keys never reach it);
-//   4. writes the sorted unit to the caller's arrays, coalesced.
+//   2. counting-sorts on the top `b` differing bits with 2-4 bins per key (shared
+//      atomics give every key its arrival rank inside its bin, a block scan gives the
+//      bin bases);
+//   3. resolves bins that hold several different keys without moving data: the keys of
+//      such bins are parked in bin order, then every key counts the keys of its own bin
+//      that precede it (all lanes busy, no serial insertion loops); bins longer than
+//      LOCAL_RANK_MAX -- adversarial bit patterns, random keys never produce them -- are
+//      finished by a block-wide bitonic network;
+//   4. writes keys and rids to their final slots in shared memory and from there to
+//      the caller's arrays, coalesced.
 #pragma once
 #include "msb64_common.cuh"
 
@@ -20,10 +23,11 @@ namespace msb64 {
 
 constexpr int LOCAL_THREADS = 256;
 constexpr int LOCAL_ITEMS = LOCAL_CAP / LOCAL_THREADS;
-constexpr int LOCAL_BITS = 12;
-constexpr uint32_t LOCAL_INSERT_MAX = 24;       // bins up to this size: one thread, insertion sort
-constexpr size_t LOCAL_SMEM = size_t(LOCAL_CAP) * 16 + (size_t(1) << LOCAL_BITS) * 4
-			      + (LOCAL_CAP / LOCAL_INSERT_MAX + 2) * 4 + 64 * 4 + 16 * 8;
+constexpr int LOCAL_BITS = 13;                  // at most 8192 bins
+constexpr uint32_t LOCAL_RANK_MAX = 32;         // bins up to this size: rank by counting
+constexpr uint32_t LOCAL_BIG_MAX = LOCAL_CAP / LOCAL_RANK_MAX + 2;
+constexpr size_t LOCAL_SMEM = size_t(LOCAL_CAP) * 16 + ((size_t(1) << LOCAL_BITS) + 32) * 4
+			      + LOCAL_BIG_MAX * 4 + 64 * 4 + 16 * 8;
 
 // Ascending compare-exchange network for any length (bitonic merges with the first
 // step mirrored, so that the missing tail behaves like +infinity).
@@ -49,7 +53,7 @@ __device__ __forceinline__ void block_bitonic(uint64_t *k, uint64_t *r, const ui
 	}
 }
 
-__global__ void __launch_bounds__(LOCAL_THREADS)
+__global__ void __launch_bounds__(LOCAL_THREADS, 2)
 local_sort_kernel(const Ctx c)
 {
 	constexpr int THREADS = LOCAL_THREADS, ITEMS = LOCAL_ITEMS;
@@ -57,8 +61,8 @@ local_sort_kernel(const Ctx c)
 	uint64_t *skeys = reinterpret_cast<uint64_t *>(smem_raw);        // [LOCAL_CAP]
 	uint64_t *srids = skeys + LOCAL_CAP;                             // [LOCAL_CAP]
 	uint32_t *bins = reinterpret_cast<uint32_t *>(srids + LOCAL_CAP);// [1 << LOCAL_BITS]
-	uint32_t *big = bins + (1u << LOCAL_BITS);                       // long bins: base | size << 16
-	uint32_t *scratch = big + (LOCAL_CAP / LOCAL_INSERT_MAX + 2);    // [64]
+	uint32_t *big = bins + (1u << LOCAL_BITS) + 32;                  // long bins: base | size << 16
+	uint32_t *scratch = big + LOCAL_BIG_MAX;                         // [64]
 	uint64_t *wor = reinterpret_cast<uint64_t *>(scratch + 64);      // [16]
 	__shared__ uint32_t s_nbig;
 
@@ -84,9 +88,8 @@ local_sort_kernel(const Ctx c)
 			const uint32_t i = j * THREADS + tid;
 			r[j] = i < size ? ld_stream_u64(src_rids + i) : 0;
 		}
-		const uint64_t first = __shfl_sync(0xffffffffu, k[0], 0);   // warp 0: element 0
 		if (tid == 0) {
-			wor[8] = first;
+			wor[8] = k[0];
 			s_nbig = 0;
 		}
 		__syncthreads();
@@ -95,8 +98,8 @@ local_sort_kernel(const Ctx c)
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j)
 			if (uint32_t(j * THREADS + tid) < size) diff |= k[j] ^ k0;
-		uint32_t dlo = __reduce_or_sync(0xffffffffu, uint32_t(diff));
-		uint32_t dhi = __reduce_or_sync(0xffffffffu, uint32_t(diff >> 32));
+		const uint32_t dlo = __reduce_or_sync(0xffffffffu, uint32_t(diff));
+		const uint32_t dhi = __reduce_or_sync(0xffffffffu, uint32_t(diff >> 32));
 		if (lane == 0) wor[warp] = (uint64_t(dhi) << 32) | dlo;
 		__syncthreads();
 		diff = 0;
@@ -119,95 +122,112 @@ local_sort_kernel(const Ctx c)
 			continue;
 		}
 
-		// 2. counting sort on the top differing bits
+		// 2. counting sort on the top differing bits, 2-4 bins per key
 		const int top = 63 - __clzll(diff);                      // highest differing bit
-		int b = 32 - __clz(size - 1);                            // ~log2(size) bins ...
-		b = min(max(b + 1, 5), LOCAL_BITS);                      // ... times two
+		int b = 32 - __clz(size - 1);                            // ceil(log2(size))
+		b = min(max(b + 1, 5), LOCAL_BITS);
 		b = min(b, top + 1);
 		const int shift = top + 1 - b;
 		const uint32_t nb = 1u << b, dmask = nb - 1;
+		// bin table transposed so that the scan below is bank-conflict free: thread t owns
+		// the `per` consecutive digits t*per .. t*per+per-1 and keeps them at q*THREADS + t
+		const int lper = max(b - 8, 0);                          // log2(bins per thread)
+		const uint32_t per = 1u << lper, pmask = per - 1;
+#define MSB64_BIN_SLOT(d) ((((d) & pmask) << 8) | ((d) >> lper))
+		// do the digit bits cover every differing bit?  then equal digit = equal key
+		const bool resolved = (diff & ((1ull << shift) - 1)) == 0;
 
-		for (uint32_t i = tid; i < nb; i += THREADS) bins[i] = 0;
+		static_assert(THREADS == 256, "MSB64_BIN_SLOT assumes 256 threads");
+		for (uint32_t i = tid; i < max(nb, uint32_t(THREADS)); i += THREADS) bins[i] = 0;
 		__syncthreads();
+		// branch-free (see tile_ranks in msb64_scatter.cuh): slots past the unit's end count
+		// into per-lane dummy bins behind the table
 		uint32_t rank[ITEMS];
+		uint32_t *dummy = bins + (1u << LOCAL_BITS) + lane;
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j) {
 			const uint32_t i = j * THREADS + tid;
-			if (i < size) rank[j] = atomicAdd(&bins[uint32_t(k[j] >> shift) & dmask], 1u);
+			const uint32_t d = uint32_t(k[j] >> shift) & dmask;
+			uint32_t *slot = i < size ? &bins[MSB64_BIN_SLOT(d)] : dummy;
+			rank[j] = atomicAdd(slot, 1u);
 		}
 		__syncthreads();
-		// exclusive scan over bins (thread handles nb/THREADS consecutive bins), pack base | count << 16
+		// exclusive scan over bins in digit order; pack base | count << 16
 		{
-			constexpr uint32_t MAXPER = (1u << LOCAL_BITS) / THREADS;
-			const uint32_t per = (nb + THREADS - 1) / THREADS;
-			uint32_t cnt[MAXPER], sum = 0;
-#pragma unroll
-			for (uint32_t q = 0; q < MAXPER; ++q) {
-				const uint32_t bi = tid * per + q;
-				cnt[q] = (q < per && bi < nb) ? bins[bi] : 0;
-				sum += cnt[q];
-			}
+			uint32_t sum = 0;
+			for (uint32_t q = 0; q < per; ++q) sum += bins[q * THREADS + tid];
 			uint32_t total;
 			uint32_t base = block_exclusive_scan<THREADS>(sum, scratch, &total);
-#pragma unroll
-			for (uint32_t q = 0; q < MAXPER; ++q) {
-				const uint32_t bi = tid * per + q;
-				if (q < per && bi < nb) {
-					bins[bi] = base | (cnt[q] << 16);
-					base += cnt[q];
-				}
+			for (uint32_t q = 0; q < per; ++q) {
+				const uint32_t cnt = bins[q * THREADS + tid];
+				bins[q * THREADS + tid] = base | (cnt << 16);
+				base += cnt;
 			}
 		}
 		__syncthreads();
+
+		// 3a. park the keys of bins that need ordering (bin base + arrival rank);
+		//     rank[] becomes base | count << 13 | min(arrival rank, 63) << 26
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j) {
 			const uint32_t i = j * THREADS + tid;
 			if (i < size) {
-				const uint32_t p = (bins[uint32_t(k[j] >> shift) & dmask] & 0xffffu) + rank[j];
-				skeys[p] = k[j];
-				srids[p] = r[j];
+				const uint32_t d = uint32_t(k[j] >> shift) & dmask;
+				const uint32_t pk = bins[MSB64_BIN_SLOT(d)];
+				const uint32_t base = pk & 0xffffu, cnt = pk >> 16;
+				if (!resolved && cnt > 1) skeys[base + rank[j]] = k[j];
+				rank[j] = (base + (resolved || cnt == 1 || cnt > LOCAL_RANK_MAX ? rank[j] : 0u))
+					  | (cnt << 13) | (min(rank[j], 63u) << 26);
 			}
 		}
 		__syncthreads();
-
-		// 3. bins that may still hold different keys
-		if (shift > 0) {
-			for (uint32_t bi = tid; bi < nb; bi += THREADS) {
-				const uint32_t packed = bins[bi];
-				const uint32_t base = packed & 0xffffu, cnt = packed >> 16;
-				if (cnt < 2) continue;
-				if (cnt <= LOCAL_INSERT_MAX) {
-					for (uint32_t i = base + 1; i < base + cnt; ++i) {
-						const uint64_t key = skeys[i];
-						if (key >= skeys[i - 1]) continue;
-						const uint64_t rid = srids[i];
-						uint32_t j = i;
-						do {
-							skeys[j] = skeys[j - 1];
-							srids[j] = srids[j - 1];
-							--j;
-						} while (j > base && key < skeys[j - 1]);
-						skeys[j] = key;
-						srids[j] = rid;
+		// 3b. final slot = bin base + number of keys of the bin that go before this one
+#pragma unroll
+		for (int j = 0; j < ITEMS; ++j) {
+			const uint32_t i = j * THREADS + tid;
+			if (i < size) {
+				const uint32_t base = rank[j] & 0x1fffu, cnt = (rank[j] >> 13) & 0x1fffu;
+				const uint32_t arrival = rank[j] >> 26;
+				uint32_t slot = base;                      // already final unless ...
+				if (!resolved && cnt > 1) {
+					if (cnt <= LOCAL_RANK_MAX) {
+						uint32_t before = 0;
+						for (uint32_t q = 0; q < cnt; ++q) {
+							const uint64_t other = skeys[base + q];
+							before += (other < k[j]) || (other == k[j] && q < arrival);
+						}
+						slot = base + before;
+					} else if (arrival == 0) {
+						big[atomicAdd(&s_nbig, 1u)] = (base) | (cnt << 16);
 					}
-				} else {
-					big[atomicAdd(&s_nbig, 1u)] = packed;
 				}
-			}
-			__syncthreads();
-			const uint32_t nbig = s_nbig;
-			for (uint32_t q = 0; q < nbig; ++q) {
-				const uint32_t packed = big[q];
-				block_bitonic(skeys + (packed & 0xffffu), srids + (packed & 0xffffu), packed >> 16);
+				rank[j] = slot;
 			}
 		}
+		__syncthreads();
+		// 4a. final slots
+#pragma unroll
+		for (int j = 0; j < ITEMS; ++j) {
+			const uint32_t i = j * THREADS + tid;
+			if (i < size) {
+				skeys[rank[j]] = k[j];
+				srids[rank[j]] = r[j];
+			}
+		}
+		__syncthreads();
+		const uint32_t nbig = s_nbig;
+		for (uint32_t q = 0; q < nbig; ++q) {
+			const uint32_t pk = big[q];
+			block_bitonic(skeys + (pk & 0xffffu), srids + (pk & 0xffffu), pk >> 16);
+		}
 
-		// 4. home
+		// 4b. home
 		for (uint32_t i = tid; i < size; i += THREADS) {
 			st_stream_u64(dst_keys + i, skeys[i]);
 			st_stream_u64(dst_rids + i, srids[i]);
 		}
 		__syncthreads();
+#undef MSB64_BIN_SLOT
 	}
 }
 

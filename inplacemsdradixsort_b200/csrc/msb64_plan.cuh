@@ -1,10 +1,10 @@
 // msb64_plan.cuh -- the recursion of local_radixsort (msb_64.c:1007-1035) as device-side
 // work lists: no host round trip between levels.
 //
-// After the histogram of level L, one block per segment
+// After the histogram of level L, one WARP per segment
 //   - scans the segment's bin counts into the write cursors of the scatter kernel
 //     (the "device-wide exclusive scan" is per segment and segments are independent,
-//     so it is a block scan);
+//     so it is a warp scan over chunks of 32 bins);
 //   - detects a degenerate digit (all keys in one bin, msb_64.c has no such shortcut):
 //     the scatter is skipped and the segment moves to the next level where it is;
 //   - files every child bucket for the next step: buckets above LOCAL_CAP become
@@ -19,7 +19,6 @@
 namespace msb64 {
 
 constexpr int PLAN_THREADS = 256;
-constexpr int PLAN_MAX_BPT = (1 << MAX_BITS) / PLAN_THREADS;
 
 // First kernel of a sort: control block, level-0 segment, its tiles and histogram.
 __global__ void init_kernel(const Ctx c, const int bits0)
@@ -54,139 +53,148 @@ __global__ void init_kernel(const Ctx c, const int bits0)
 	}
 }
 
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v)
+{
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+		if (lane_id() >= d) v += t;
+	}
+	return v;
+}
+
+// Whole warp: make [begin, begin+size) in buffer `buf` a segment of level+1.
+__device__ __forceinline__ void emit_segment(const Ctx &c, Control *ctl, Seg *segs_out,
+					     Tile *tiles_out, uint32_t *hist_out, int level,
+					     uint32_t nbn, uint32_t begin, uint32_t size, uint32_t buf)
+{
+	const uint32_t lane = lane_id();
+	const uint32_t nt = seg_tile_count(begin, size);
+	uint32_t child = 0, tile_at = 0;
+	if (lane == 0) {
+		child = atomicAdd(&ctl->nsegs[level + 1], 1u);
+		tile_at = atomicAdd(&ctl->ntiles[level + 1], nt);
+		if (child >= c.max_segs) atomicOr(&ctl->error, 1u);
+		else segs_out[child] = Seg{begin, size, buf, 0u};
+		if (tile_at + nt > c.max_tiles) atomicOr(&ctl->error, 2u);
+	}
+	child = __shfl_sync(0xffffffffu, child, 0);
+	tile_at = __shfl_sync(0xffffffffu, tile_at, 0);
+	if (child >= c.max_segs || tile_at + nt > c.max_tiles) return;
+	for (uint32_t j = lane; j < nbn; j += 32) hist_out[size_t(child) * nbn + j] = 0;
+	for (uint32_t j = lane; j < nt; j += 32) tiles_out[tile_at + j] = Tile{child, j};
+}
+
+// Whole warp: final data of [begin, begin+size) sits in B, schedule its copy to A.
+__device__ __forceinline__ void emit_copy(const Ctx &c, Control *ctl, uint32_t begin, uint32_t size)
+{
+	const uint32_t lane = lane_id();
+	const uint32_t nc = (size + COPY_TILE - 1) / COPY_TILE;
+	uint32_t at = 0;
+	if (lane == 0) {
+		at = atomicAdd(&ctl->ncopies, nc);
+		if (at + nc > c.max_copies) atomicOr(&ctl->error, 8u);
+	}
+	at = __shfl_sync(0xffffffffu, at, 0);
+	if (at + nc > c.max_copies) return;
+	for (uint32_t j = lane; j < nc; j += 32) {
+		const uint32_t off = j * COPY_TILE;
+		c.copies[at + j] = CopyTile{begin + off, min(COPY_TILE, size - off)};
+	}
+}
+
 // bits: digit width of this level; next_bits: of the next level (0 = this is the last).
 __global__ void __launch_bounds__(PLAN_THREADS)
 plan_kernel(const Ctx c, const int level, const int bits, const int next_bits)
 {
-	constexpr int THREADS = PLAN_THREADS;
-	__shared__ uint32_t s_cnt[1 << MAX_BITS];
-	__shared__ uint32_t s_beg[1 << MAX_BITS];
-	__shared__ uint32_t s_scratch[THREADS / 32 + 1];
-	__shared__ uint32_t s_large[1 << MAX_BITS];     // bins that become segments
-	__shared__ uint32_t s_nlarge, s_max, s_seg_base, s_tile_base, s_copy_base;
-
-	const uint32_t tid = threadIdx.x;
+	const uint32_t lane = lane_id();
+	const uint32_t warps_per_block = PLAN_THREADS / 32;
 	const uint32_t NB = 1u << bits, NBN = next_bits ? (1u << next_bits) : 0u;
-	const uint32_t BPT = (NB + THREADS - 1) / THREADS;
 	Control *ctl = c.ctl;
-	Seg *segs = ((level & 1) ? c.segs[1] : c.segs[0]), *segs_out = ((level & 1) ? c.segs[0] : c.segs[1]);
-	Tile *tiles_out = ((level & 1) ? c.tiles[0] : c.tiles[1]);
-	uint32_t *hist = ((level & 1) ? c.hist[1] : c.hist[0]), *hist_out = ((level & 1) ? c.hist[0] : c.hist[1]);
-	const uint32_t nsegs = ctl->nsegs[level];
+	Seg *segs = (level & 1) ? c.segs[1] : c.segs[0];
+	Seg *segs_out = (level & 1) ? c.segs[0] : c.segs[1];
+	Tile *tiles_out = (level & 1) ? c.tiles[0] : c.tiles[1];
+	uint32_t *hist = (level & 1) ? c.hist[1] : c.hist[0];
+	uint32_t *hist_out = (level & 1) ? c.hist[0] : c.hist[1];
+	const uint32_t nsegs = min(ctl->nsegs[level], c.max_segs);
 	const bool last = next_bits == 0;
 
-	for (uint32_t sg = blockIdx.x; sg < nsegs; sg += gridDim.x) {
+	for (uint32_t sg = blockIdx.x * warps_per_block + (threadIdx.x >> 5); sg < nsegs;
+	     sg += gridDim.x * warps_per_block) {
 		const Seg s = segs[sg];
 		uint32_t *h = hist + size_t(sg) * NB;
-		if (tid == 0) {
-			s_nlarge = 0;
-			s_max = 0;
-		}
-		__syncthreads();
 
-		// counts -> exclusive begins (bins tid*BPT .. tid*BPT+BPT-1)
-		uint32_t cnt[PLAN_MAX_BPT], sum = 0, mx = 0;
-#pragma unroll
-		for (int q = 0; q < PLAN_MAX_BPT; ++q) {
-			const uint32_t b = tid * BPT + q;
-			cnt[q] = (q < BPT && b < NB) ? h[b] : 0;
-			sum += cnt[q];
-			mx = max(mx, cnt[q]);
-		}
-		uint32_t total;
-		uint32_t base = block_exclusive_scan<THREADS>(sum, s_scratch, &total);
-		atomicMax(&s_max, mx);
-		__syncthreads();
-		const bool degenerate = s_max == s.size;
-		const uint32_t dst_buf = degenerate ? s.buf : (s.buf ^ 1u);
-
-#pragma unroll
-		for (int q = 0; q < PLAN_MAX_BPT; ++q) {
-			const uint32_t b = tid * BPT + q;
-			if (q < BPT && b < NB) {
-				const uint32_t beg = s.begin + base;
-				s_cnt[b] = cnt[q];
-				s_beg[b] = beg;
-				h[b] = beg;                       // write cursor of bin b
-				base += cnt[q];
-				if (!last && cnt[q] > LOCAL_CAP) s_large[atomicAdd(&s_nlarge, 1u)] = b;
-			}
-		}
-		__syncthreads();
-
-		if (tid == 0) {
-			if (degenerate) {
+		// pass 1: is the digit degenerate (one bin holds the whole segment)?
+		uint32_t mx = 0;
+		for (uint32_t b = lane; b < NB; b += 32) mx = max(mx, h[b]);
+		mx = __reduce_max_sync(0xffffffffu, mx);
+		if (mx == s.size) {
+			if (lane == 0) {
 				segs[sg].skip = 1;
 				atomicAdd(&ctl->degenerate, 1u);
-			} else {
-				atomicAdd(&ctl->moved[level], s.size);
 			}
-			if (!last) {
-				// greedy merge of neighbouring small buckets into units
-				uint32_t run_beg = 0, run_size = 0, local_pairs = 0;
-				for (uint32_t b = 0; b <= NB; ++b) {
-					const uint32_t cb = b < NB ? s_cnt[b] : 0xffffffffu;
-					if (cb == 0) continue;
-					if (cb > LOCAL_CAP || run_size + cb > LOCAL_CAP) {
-						if (run_size) {
-							const uint32_t u = atomicAdd(&ctl->nunits, 1u);
-							if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, 0u};
-							else atomicOr(&ctl->error, 4u);
-							local_pairs += run_size;
-						}
-						run_size = 0;
-						if (cb > LOCAL_CAP) continue;
-					}
-					if (run_size == 0) run_beg = s_beg[b];
-					run_size += cb;
-				}
-				if (local_pairs) atomicAdd(&ctl->local_pairs, local_pairs);
-				// reserve segment slots and tiles for the large children
-				uint32_t nt = 0;
-				for (uint32_t i = 0; i < s_nlarge; ++i) {
-					const uint32_t b = s_large[i];
-					nt += seg_tile_count(s_beg[b], s_cnt[b]);
-				}
-				s_seg_base = atomicAdd(&ctl->nsegs[level + 1], s_nlarge);
-				s_tile_base = atomicAdd(&ctl->ntiles[level + 1], nt);
-				if (s_seg_base + s_nlarge > c.max_segs) atomicOr(&ctl->error, 1u);
-				if (s_tile_base + nt > c.max_tiles) atomicOr(&ctl->error, 2u);
-			} else if (dst_buf == 1u) {
-				// final data ends in the scratch buffer: copy it home
-				const uint32_t nc = (s.size + COPY_TILE - 1) / COPY_TILE;
-				s_copy_base = atomicAdd(&ctl->ncopies, nc);
-				if (s_copy_base + nc > c.max_copies) atomicOr(&ctl->error, 8u);
-			}
+			if (!last)
+				emit_segment(c, ctl, segs_out, tiles_out, hist_out, level, NBN, s.begin, s.size, s.buf);
+			else if (s.buf == 1u)
+				emit_copy(c, ctl, s.begin, s.size);
+			continue;
 		}
-		__syncthreads();
+		const uint32_t dst_buf = s.buf ^ 1u;
+		if (lane == 0) atomicAdd(&ctl->moved[level], s.size);
 
-		if (!last) {
-			const uint32_t nlarge = s_nlarge;
-			if (s_seg_base + nlarge <= c.max_segs) {
-				uint32_t tile_at = s_tile_base;
-				for (uint32_t i = 0; i < nlarge; ++i) {
-					const uint32_t b = s_large[i];
-					const uint32_t child = s_seg_base + i;
-					const uint32_t nt = seg_tile_count(s_beg[b], s_cnt[b]);
-					if (tid == 0) segs_out[child] = Seg{s_beg[b], s_cnt[b], dst_buf, 0u};
-					for (uint32_t j = tid; j < NBN; j += THREADS)
-						hist_out[size_t(child) * NBN + j] = 0;
-					if (tile_at + nt <= c.max_tiles)
-						for (uint32_t j = tid; j < nt; j += THREADS)
-							tiles_out[tile_at + j] = Tile{child, j};
-					tile_at += nt;
-				}
+		// pass 2: cursors, children
+		uint32_t base = s.begin;
+		uint32_t run_beg = 0, run_size = 0, local_pairs = 0;      // warp-uniform merge state
+		for (uint32_t b0 = 0; b0 < NB; b0 += 32) {
+			const uint32_t b = b0 + lane;
+			const uint32_t cnt = b < NB ? h[b] : 0;
+			const uint32_t inc = warp_inclusive_scan(cnt);
+			const uint32_t beg = base + inc - cnt;
+			if (b < NB) h[b] = beg;                       // write cursor of bin b
+			base += __shfl_sync(0xffffffffu, inc, 31);
+			if (last) continue;
+
+			// buckets too large for shared memory: segments of the next level
+			uint32_t large = __ballot_sync(0xffffffffu, cnt > LOCAL_CAP);
+			while (large) {
+				const int src = __ffs(large) - 1;
+				large &= large - 1;
+				emit_segment(c, ctl, segs_out, tiles_out, hist_out, level, NBN,
+					     __shfl_sync(0xffffffffu, beg, src),
+					     __shfl_sync(0xffffffffu, cnt, src), dst_buf);
 			}
-		} else if (dst_buf == 1u) {
-			const uint32_t nc = (s.size + COPY_TILE - 1) / COPY_TILE;
-			if (s_copy_base + nc <= c.max_copies)
-				for (uint32_t j = tid; j < nc; j += THREADS) {
-					const uint32_t off = j * COPY_TILE;
-					c.copies[s_copy_base + j] =
-						CopyTile{s.begin + off, min(COPY_TILE, s.size - off)};
+			// greedy merge of neighbouring small buckets into units (all lanes in step)
+			uint32_t present = __ballot_sync(0xffffffffu, cnt != 0);
+			while (present) {
+				const int src = __ffs(present) - 1;
+				present &= present - 1;
+				const uint32_t cb = __shfl_sync(0xffffffffu, cnt, src);
+				const uint32_t bb = __shfl_sync(0xffffffffu, beg, src);
+				if (cb > LOCAL_CAP || run_size + cb > LOCAL_CAP) {
+					if (run_size && lane == 0) {
+						const uint32_t u = atomicAdd(&ctl->nunits, 1u);
+						if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, 0u};
+						else atomicOr(&ctl->error, 4u);
+					}
+					local_pairs += run_size;
+					run_size = 0;
+					if (cb > LOCAL_CAP) continue;
 				}
+				if (run_size == 0) run_beg = bb;
+				run_size += cb;
+			}
 		}
-		__syncthreads();
+		if (!last) {
+			if (run_size && lane == 0) {
+				const uint32_t u = atomicAdd(&ctl->nunits, 1u);
+				if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, 0u};
+				else atomicOr(&ctl->error, 4u);
+			}
+			local_pairs += run_size;
+			if (local_pairs && lane == 0) atomicAdd(&ctl->local_pairs, local_pairs);
+		} else if (dst_buf == 1u) {
+			emit_copy(c, ctl, s.begin, s.size);           // final data ends in the scratch buffer
+		}
 	}
 }
 
@@ -194,7 +202,7 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits)
 __global__ void __launch_bounds__(256)
 copy_kernel(const Ctx c)
 {
-	const uint32_t ncopies = c.ctl->ncopies;
+	const uint32_t ncopies = min(c.ctl->ncopies, c.max_copies);
 	for (uint32_t t = blockIdx.x; t < ncopies; t += gridDim.x) {
 		const CopyTile ct = c.copies[t];
 		for (uint32_t i = threadIdx.x; i < ct.size; i += blockDim.x) {

@@ -51,7 +51,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # MSB64_B200_LIB: developer override used to compare tuning variants of the library
+    return os.environ.get("MSB64_B200_LIB") or _build.LIB_PATH
 
 
 def load_library() -> C.CDLL:
