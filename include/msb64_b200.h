@@ -158,6 +158,27 @@ int msb64_b200_fill(uint64_t *d_keys, uint64_t *d_rids, uint64_t n,
 int msb64_b200_check(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
 		     uint64_t *out, void *stream);
 
+/* ------------------------------------------- 4. multi-GPU range partition steps
+ *
+ * The device halves of the cross-GPU range partition (the role of the reference's
+ * sample / range_histogram / partition phase across NUMA nodes, msb_64.c:239-351,
+ * 497-699, 1546-1606); the collectives between them are the caller's
+ * (inplacemsdradixsort_b200/distributed.py uses NCCL through torch.distributed).
+ *
+ * msb64_b200_digit_histogram: d_hist[0 .. 2^bits) = number of keys whose bits
+ *   [shift, shift+bits) equal the index (bits <= 12).  d_hist is zeroed first.
+ * msb64_b200_route: groups the n pairs by destination = d_bin_to_dest[digit] (one byte
+ *   per bin, ndest <= 64 destinations) into d_out_keys / d_out_rids; d_cursors[dest]
+ *   must hold the first output slot of each destination (exclusive prefix of the
+ *   per-destination counts) and is advanced by the kernel.  Order inside a
+ *   destination is unspecified. */
+int msb64_b200_digit_histogram(const uint64_t *d_keys, uint64_t n, int shift, int bits,
+			       uint64_t *d_hist, void *stream);
+int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
+		     int shift, int bits, const uint8_t *d_bin_to_dest, int ndest,
+		     uint32_t *d_cursors, uint64_t *d_out_keys, uint64_t *d_out_rids,
+		     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

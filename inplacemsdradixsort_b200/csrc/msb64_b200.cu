@@ -25,6 +25,7 @@
 #include "msb64_histogram.cuh"
 #include "msb64_local_sort.cuh"
 #include "msb64_plan.cuh"
+#include "msb64_route.cuh"
 #include "msb64_scatter.cuh"
 
 using namespace msb64;
@@ -631,6 +632,51 @@ int msb64_b200_last_level_times(uint64_t *out, int cap)
 	for (int l = 0; l < g_dev.last_levels; ++l)
 		for (int j = 0; j < 3 && k < cap; ++j) out[k++] = g_dev.level_us[l][j];
 	return k;
+}
+
+int msb64_b200_digit_histogram(const uint64_t *d_keys, uint64_t n, int shift, int bits,
+				uint64_t *d_hist, void *stream)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	int rc = device_init();
+	if (rc) return rc;
+	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift + bits > 64 || !d_hist)
+		return fail(MSB64_ERR_ARG, "digit_histogram: bad shift/bits%s");
+	if (n > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) << bits, st));
+	if (n) {
+		digit_histogram_kernel<<<g_dev.sms * 8, 256, sizeof(uint32_t) << bits, st>>>(
+			d_keys, n, shift, bits, reinterpret_cast<unsigned long long *>(d_hist));
+		g_launches += 1;
+	}
+	CUDA_TRY(cudaGetLastError());
+	return MSB64_OK;
+}
+
+int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, int shift, int bits,
+		     const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors,
+		     uint64_t *d_out_keys, uint64_t *d_out_rids, void *stream)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	int rc = device_init();
+	if (rc) return rc;
+	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift + bits > 64 || ndest < 1 ||
+	    ndest > ROUTE_MAX_DEST || !d_bin_to_dest || !d_cursors)
+		return fail(MSB64_ERR_ARG, "route: bad shift/bits/ndest%s");
+	if (n > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
+	if (!n) return MSB64_OK;
+	static bool configured = false;
+	if (!configured) {
+		CUDA_TRY(cudaFuncSetAttribute(route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					      int(route_smem(ROUTE_MAX_BITS))));
+		configured = true;
+	}
+	route_kernel<<<g_dev.sms * 2, ROUTE_THREADS, route_smem(bits), static_cast<cudaStream_t>(stream)>>>(
+		d_keys, d_rids, uint32_t(n), shift, bits, d_bin_to_dest, ndest, d_cursors, d_out_keys, d_out_rids);
+	g_launches += 1;
+	CUDA_TRY(cudaGetLastError());
+	return MSB64_OK;
 }
 
 void *msb64_b200_host_alloc(size_t bytes)

@@ -38,6 +38,7 @@ EXPORTS = (
     "msb64_b200_host_free", "msb64_b200_device_alloc", "msb64_b200_device_free",
     "msb64_b200_memcpy_h2d", "msb64_b200_memcpy_d2h", "msb64_b200_memcpy_d2d",
     "msb64_b200_stream_sync", "msb64_b200_fill", "msb64_b200_check",
+    "msb64_b200_digit_histogram", "msb64_b200_route",
 )
 
 
@@ -108,6 +109,12 @@ def load_library() -> C.CDLL:
                                   C.c_uint64, C.c_void_p]
     L.msb64_b200_check.restype = C.c_int
     L.msb64_b200_check.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u64p, C.c_void_p]
+    L.msb64_b200_digit_histogram.restype = C.c_int
+    L.msb64_b200_digit_histogram.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p]
+    L.msb64_b200_route.restype = C.c_int
+    L.msb64_b200_route.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

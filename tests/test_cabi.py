@@ -1,0 +1,102 @@
+"""The C-ABI library without a GPU: it loads, exports every symbol include/msb64_b200.h
+declares, keeps the reference's signatures, and refuses to compute without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "msb64_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)
+    skip = {"defined", "if", "sizeof"}
+    return sorted({n for n in names if n not in skip and not n.isupper()})
+
+
+def test_header_and_library_agree(msb):
+    lib = msb.load_library()
+    declared = declared_functions()
+    assert "sort" in declared and "mamalloc" in declared
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, f"declared but not exported: {missing}"
+    assert sorted(msb.EXPORTS) == declared, "msb64.EXPORTS is out of date with the header"
+
+
+def test_reference_signatures_are_kept():
+    """sort() and mamalloc() read exactly like reference include/msb_64.h:36-40."""
+    text = re.sub(r"\s+", " ", open(HEADER).read())
+    assert ("void sort(uint64_t **keys, uint64_t **rids, uint64_t *size, int threads, int numa, "
+            "double fudge, char **description, uint64_t *times);") in text
+    assert "void *mamalloc(size_t size);" in text
+
+
+def test_library_is_sm100a_only(msb):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", msb.library_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_mamalloc_alignment(msb):
+    a = msb.mamalloc(1000)
+    assert a.ctypes.data % 64 == 0 and a.size == 1000
+    a[:] = 7
+    msb.mafree(a)
+
+
+def test_no_cpu_fallback(msb):
+    """Without a device every compute entry point reports MSB64_ERR_CUDA; nothing sorts."""
+    if msb.device_count() > 0:
+        pytest.skip("a GPU is visible; the refusal path is for CPU-only boxes")
+    k = np.array([3, 1, 2], dtype=np.uint64)
+    r = np.arange(3, dtype=np.uint64)
+    with pytest.raises(msb.Msb64Error) as e:
+        msb.sort_pairs(k, r)
+    assert e.value.code == -1
+    assert k.tolist() == [3, 1, 2], "input must be untouched"
+    with pytest.raises(msb.Msb64Error):
+        msb.sort([k], [r], [3])
+
+
+def test_product_does_not_touch_the_oracle():
+    """The package and the CUDA sources never import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "inplacemsdradixsort_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "liboracle" not in text and "from oracle" not in text \
+                    and "import oracle" not in text and "msb64_oracle" not in text, f
+    assert "oracle" not in open(HEADER).read().lower()
+
+
+def test_schedule_api(msb):
+    for e in range(0, 33):
+        s = msb.get_schedule(1 << e)
+        assert sum(s) == 64 and all(4 <= b <= 11 for b in s) and len(s) <= 16, (e, s)
+    msb.set_schedule([8] * 8)
+    assert msb.get_schedule(12345) == [8] * 8
+    msb.set_schedule(None)
+    for bad in ([8] * 7, [3] + [8] * 7 + [5], [12, 12, 12, 12, 12, 4]):
+        with pytest.raises(msb.Msb64Error):
+            msb.set_schedule(bad)
+    assert msb.get_schedule(1 << 30)[:3] == [7, 6, 6]
+
+
+def test_workspace_bytes(msb):
+    prev = 0
+    for e in (10, 16, 20, 24, 28, 30):
+        w = msb.workspace_bytes(1 << e)
+        assert w >= 2 * 8 * (1 << e) and w > prev
+        prev = w
+    assert msb.workspace_bytes(1 << 30) < 2.2 * 16 * (1 << 30)
