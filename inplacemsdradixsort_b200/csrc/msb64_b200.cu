@@ -223,7 +223,7 @@ void launch_level(const Ctx &c, int level, int shift, int next_bits, cudaStream_
 	if (ev) cudaEventRecord(ev[0], st);
 	histogram_kernel<BITS, 256><<<g_dev.sms * g_dev.hist_blocks[BITS], 256, H::SMEM, st>>>(c, level, shift);
 	if (ev) cudaEventRecord(ev[1], st);
-	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits);
+	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits, shift);
 	if (ev) cudaEventRecord(ev[2], st);
 	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<g_dev.sms * g_dev.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, shift);
 	if (ev) cudaEventRecord(ev[3], st);

@@ -43,8 +43,21 @@ struct Unit {
 	uint32_t begin;
 	uint32_t size;    // 1..LOCAL_CAP
 	uint32_t buf;     // where the pairs are now; they are always written to A
-	uint32_t pad;
+	uint32_t origin;  // unit_origin(): digit position and first digit of the run of buckets
 };
+
+// A unit is a run of buckets with consecutive digits first, first+1, ... at bit position
+// `shift`: its keys lie in a contiguous key range that starts at prefix | first << shift.
+// The local sort subtracts that origin so that the keys of a unit made of several
+// buckets spread evenly over its counting bins.
+__host__ __device__ inline uint32_t unit_origin(int shift, uint32_t first_digit)
+{
+	return uint32_t(shift) | (first_digit << 8);
+}
+__host__ __device__ inline uint64_t unit_origin_key(uint32_t origin)
+{
+	return uint64_t(origin >> 8) << (origin & 63u);
+}
 
 struct CopyTile {
 	uint32_t begin;

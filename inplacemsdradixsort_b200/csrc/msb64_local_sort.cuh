@@ -4,30 +4,35 @@
 //
 // A unit is a run of neighbouring buckets of at most LOCAL_CAP pairs.  Its keys agree
 // on some prefix and may differ anywhere below; the block
-//   1. loads keys and rids (coalesced) and ORs together key ^ first_key: the set bits
-//      are exactly the bit positions in which the unit's keys differ;
-//   2. counting-sorts on the top `b` differing bits with 2-4 bins per key (shared
-//      atomics give every key its arrival rank inside its bin, a block scan gives the
-//      bin bases);
-//   3. resolves bins that hold several different keys without moving data: the keys of
-//      such bins are parked in bin order, then every key counts the keys of its own bin
-//      that precede it (all lanes busy, no serial insertion loops); bins longer than
-//      LOCAL_RANK_MAX -- adversarial bit patterns, random keys never produce them -- are
-//      finished by a block-wide bitonic network;
-//   4. writes keys and rids to their final slots in shared memory and from there to
-//      the caller's arrays, coalesced.
+//   1. loads keys and rids (coalesced) and reduces OR and AND of the keys: the bits in
+//      which the unit's keys differ are exactly OR & ~AND;
+//   2. counting-sorts on the top `b` differing bits with 1-2 bins per key: a shared
+//      atomic gives every key its arrival rank inside its bin, a block scan over the
+//      bin counts (16-byte shared loads, 4 bins each) gives the bin bases, and every
+//      pair goes straight to base + arrival rank in the staging arrays;
+//   3. bins that hold several different keys are rare and short (Poisson with mean
+//      <= 1): the first arrival files the bin in a dense list, and afterwards ONE thread
+//      per listed bin orders its few pairs in place by insertion -- all lanes of a warp
+//      work on colliding bins, instead of every key looping over its bin mates behind
+//      a divergent branch.  Bins longer than LOCAL_SERIAL_MAX (adversarial bit
+//      patterns; random keys never produce them) are finished by a block-wide bitonic
+//      network;
+//   4. writes keys and rids from the staging arrays to the caller's arrays, coalesced.
 #pragma once
 #include "msb64_common.cuh"
 
 namespace msb64 {
 
-constexpr int LOCAL_THREADS = 256;
+constexpr int LOCAL_THREADS = 512;
 constexpr int LOCAL_ITEMS = LOCAL_CAP / LOCAL_THREADS;
-constexpr int LOCAL_BITS = 13;                  // at most 8192 bins
-constexpr uint32_t LOCAL_RANK_MAX = 32;         // bins up to this size: rank by counting
-constexpr uint32_t LOCAL_BIG_MAX = LOCAL_CAP / LOCAL_RANK_MAX + 2;
-constexpr size_t LOCAL_SMEM = size_t(LOCAL_CAP) * 16 + ((size_t(1) << LOCAL_BITS) + 32) * 4
-			      + LOCAL_BIG_MAX * 4 + 64 * 4 + 16 * 8;
+constexpr int LOCAL_BITS = 12;                  // at most 4096 bins
+constexpr uint32_t LOCAL_NBINS = 1u << LOCAL_BITS;
+constexpr uint32_t LOCAL_SERIAL_MAX = 16;       // bins up to this size: ordered by one thread
+constexpr uint32_t LOCAL_LIST_MAX = LOCAL_CAP / 2;                       // bins with >= 2 keys
+constexpr uint32_t LOCAL_BIG_MAX = LOCAL_CAP / (LOCAL_SERIAL_MAX + 1) + 2;
+constexpr size_t LOCAL_SMEM = size_t(LOCAL_CAP) * 16 + (size_t(LOCAL_NBINS) + 32) * 4
+			      + LOCAL_LIST_MAX * 4 + LOCAL_BIG_MAX * 4 + 64 * 4
+			      + 2 * (LOCAL_THREADS / 32) * 8;
 
 // Ascending compare-exchange network for any length (bitonic merges with the first
 // step mirrored, so that the missing tail behaves like +infinity).
@@ -56,15 +61,17 @@ __device__ __forceinline__ void block_bitonic(uint64_t *k, uint64_t *r, const ui
 __global__ void __launch_bounds__(LOCAL_THREADS, 2)
 local_sort_kernel(const Ctx c)
 {
-	constexpr int THREADS = LOCAL_THREADS, ITEMS = LOCAL_ITEMS;
+	constexpr int THREADS = LOCAL_THREADS, ITEMS = LOCAL_ITEMS, WARPS = THREADS / 32;
+	static_assert(THREADS == 512, "the bin layout assumes 512 threads");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint64_t *skeys = reinterpret_cast<uint64_t *>(smem_raw);        // [LOCAL_CAP]
 	uint64_t *srids = skeys + LOCAL_CAP;                             // [LOCAL_CAP]
-	uint32_t *bins = reinterpret_cast<uint32_t *>(srids + LOCAL_CAP);// [1 << LOCAL_BITS]
-	uint32_t *big = bins + (1u << LOCAL_BITS) + 32;                  // long bins: base | size << 16
+	uint32_t *bins = reinterpret_cast<uint32_t *>(srids + LOCAL_CAP);// [LOCAL_NBINS + 32]
+	uint32_t *list = bins + LOCAL_NBINS + 32;                        // short bins to order: base | size << 16
+	uint32_t *big = list + LOCAL_LIST_MAX;                           // long bins:           base | size << 16
 	uint32_t *scratch = big + LOCAL_BIG_MAX;                         // [64]
-	uint64_t *wor = reinterpret_cast<uint64_t *>(scratch + 64);      // [16]
-	__shared__ uint32_t s_nbig;
+	uint64_t *wred = reinterpret_cast<uint64_t *>(scratch + 64);     // [2 * WARPS] OR, AND per warp
+	__shared__ uint32_t s_nlist, s_nbig;
 
 	const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
 	const uint32_t nunits = min(c.ctl->nunits, c.max_units);
@@ -76,35 +83,52 @@ local_sort_kernel(const Ctx c)
 		uint64_t *dst_keys = c.keys[0] + un.begin, *dst_rids = c.rids[0] + un.begin;
 		const uint32_t size = un.size;
 
-		// 1. load; which bits differ?
+		// 1. load (slots past the end re-read the last pair: no branches, and harmless
+		//    for the OR / AND reductions); which bits differ?
 		uint64_t k[ITEMS], r[ITEMS];
 #pragma unroll
-		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			k[j] = i < size ? ld_stream_u64(src_keys + i) : 0;
-		}
-#pragma unroll
-		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			r[j] = i < size ? ld_stream_u64(src_rids + i) : 0;
-		}
-		if (tid == 0) {
-			wor[8] = k[0];
-			s_nbig = 0;
-		}
-		__syncthreads();
-		const uint64_t k0 = wor[8];
-		uint64_t diff = 0;
+		for (int j = 0; j < ITEMS; ++j)
+			k[j] = ld_stream_u64(src_keys + min(uint32_t(j * THREADS) + tid, size - 1));
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j)
-			if (uint32_t(j * THREADS + tid) < size) diff |= k[j] ^ k0;
-		const uint32_t dlo = __reduce_or_sync(0xffffffffu, uint32_t(diff));
-		const uint32_t dhi = __reduce_or_sync(0xffffffffu, uint32_t(diff >> 32));
-		if (lane == 0) wor[warp] = (uint64_t(dhi) << 32) | dlo;
-		__syncthreads();
-		diff = 0;
+			r[j] = ld_stream_u64(src_rids + min(uint32_t(j * THREADS) + tid, size - 1));
+		// the bin table is free here (the previous unit is done with it)
+		{
+			uint4 *b4 = reinterpret_cast<uint4 *>(bins);
+			for (uint32_t i = tid; i < (LOCAL_NBINS + 32) / 4; i += THREADS)
+				b4[i] = make_uint4(0u, 0u, 0u, 0u);
+		}
+		if (tid == 0) {
+			s_nlist = 0;
+			s_nbig = 0;
+		}
+		// binning value: key minus the unit's origin (monotone; see unit_origin)
+		const uint64_t origin = unit_origin_key(un.origin);
+		uint64_t vor = k[0] - origin, vand = vor;
 #pragma unroll
-		for (int w = 0; w < THREADS / 32; ++w) diff |= wor[w];
+		for (int j = 1; j < ITEMS; ++j) {
+			vor |= k[j] - origin;
+			vand &= k[j] - origin;
+		}
+		{
+			const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(vor));
+			const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(vor >> 32));
+			const uint32_t alo = __reduce_and_sync(0xffffffffu, uint32_t(vand));
+			const uint32_t ahi = __reduce_and_sync(0xffffffffu, uint32_t(vand >> 32));
+			if (lane == 0) {
+				wred[warp] = (uint64_t(ohi) << 32) | olo;
+				wred[WARPS + warp] = (uint64_t(ahi) << 32) | alo;
+			}
+		}
+		__syncthreads();
+		vor = 0;
+		vand = ~0ull;
+#pragma unroll
+		for (int w = 0; w < WARPS; ++w) {
+			vor |= wred[w];
+			vand &= wred[WARPS + w];
+		}
+		const uint64_t diff = vor & ~vand;
 
 		if (diff == 0) {
 			// all keys equal: nothing to order, only bring the pairs home
@@ -122,111 +146,116 @@ local_sort_kernel(const Ctx c)
 			continue;
 		}
 
-		// 2. counting sort on the top differing bits, 2-4 bins per key
+		// 2. counting sort on the top differing bits, 1-2 bins per key
 		const int top = 63 - __clzll(diff);                      // highest differing bit
-		int b = 32 - __clz(size - 1);                            // ceil(log2(size))
-		b = min(max(b + 1, 5), LOCAL_BITS);
+		int b = 32 - __clz(size - 1);                            // ceil(log2(size)), size >= 2 here
+		b = min(max(b, 5), LOCAL_BITS);
 		b = min(b, top + 1);
 		const int shift = top + 1 - b;
 		const uint32_t nb = 1u << b, dmask = nb - 1;
-		// bin table transposed so that the scan below is bank-conflict free: thread t owns
-		// the `per` consecutive digits t*per .. t*per+per-1 and keeps them at q*THREADS + t
-		const int lper = max(b - 8, 0);                          // log2(bins per thread)
-		const uint32_t per = 1u << lper, pmask = per - 1;
-#define MSB64_BIN_SLOT(d) ((((d) & pmask) << 8) | ((d) >> lper))
+		// thread t owns the `per` consecutive digits t*per .. t*per+per-1 (per = 4 or 8) and
+		// keeps them as 16-byte chunks at chunk index c*THREADS + t: the scan reads them
+		// with conflict-free 16-byte loads
+		const int lper = max(b - 9, 2);
+		const uint32_t pmask = (1u << lper) - 1;
+#define MSB64_BIN_SLOT(d) ((((((d) & pmask) >> 2) * THREADS + ((d) >> lper)) << 2) | ((d) & 3u))
 		// do the digit bits cover every differing bit?  then equal digit = equal key
 		const bool resolved = (diff & ((1ull << shift) - 1)) == 0;
 
-		static_assert(THREADS == 256, "MSB64_BIN_SLOT assumes 256 threads");
-		for (uint32_t i = tid; i < max(nb, uint32_t(THREADS)); i += THREADS) bins[i] = 0;
-		__syncthreads();
 		// branch-free (see tile_ranks in msb64_scatter.cuh): slots past the unit's end count
 		// into per-lane dummy bins behind the table
 		uint32_t rank[ITEMS];
-		uint32_t *dummy = bins + (1u << LOCAL_BITS) + lane;
+		uint32_t *dummy = bins + LOCAL_NBINS + lane;
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j) {
 			const uint32_t i = j * THREADS + tid;
-			const uint32_t d = uint32_t(k[j] >> shift) & dmask;
+			const uint32_t d = uint32_t((k[j] - origin) >> shift) & dmask;
 			uint32_t *slot = i < size ? &bins[MSB64_BIN_SLOT(d)] : dummy;
 			rank[j] = atomicAdd(slot, 1u);
 		}
 		__syncthreads();
-		// exclusive scan over bins in digit order; pack base | count << 16
+		// exclusive scan over bins in digit order; every bin becomes base | count << 16
 		{
-			uint32_t sum = 0;
-			for (uint32_t q = 0; q < per; ++q) sum += bins[q * THREADS + tid];
+			uint4 *b4 = reinterpret_cast<uint4 *>(bins);
+			const bool own = (tid << lper) < nb;
+			const bool two = lper == 3;
+			uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+			if (own) {
+				v0 = b4[tid];
+				if (two) v1 = b4[THREADS + tid];
+			}
+			const uint32_t sum = v0.x + v0.y + v0.z + v0.w + v1.x + v1.y + v1.z + v1.w;
 			uint32_t total;
 			uint32_t base = block_exclusive_scan<THREADS>(sum, scratch, &total);
-			for (uint32_t q = 0; q < per; ++q) {
-				const uint32_t cnt = bins[q * THREADS + tid];
-				bins[q * THREADS + tid] = base | (cnt << 16);
-				base += cnt;
+			if (own) {
+				uint4 o;
+				o.x = base | (v0.x << 16); base += v0.x;
+				o.y = base | (v0.y << 16); base += v0.y;
+				o.z = base | (v0.z << 16); base += v0.z;
+				o.w = base | (v0.w << 16); base += v0.w;
+				b4[tid] = o;
+				if (two) {
+					o.x = base | (v1.x << 16); base += v1.x;
+					o.y = base | (v1.y << 16); base += v1.y;
+					o.z = base | (v1.z << 16); base += v1.z;
+					o.w = base | (v1.w << 16);
+					b4[THREADS + tid] = o;
+				}
 			}
 		}
 		__syncthreads();
 
-		// 3a. park the keys of bins that need ordering (bin base + arrival rank);
-		//     rank[] becomes base | count << 13 | min(arrival rank, 63) << 26
+		// 3a. every pair to bin base + arrival rank; first arrivals file bins that need ordering
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j) {
 			const uint32_t i = j * THREADS + tid;
 			if (i < size) {
-				const uint32_t d = uint32_t(k[j] >> shift) & dmask;
+				const uint32_t d = uint32_t((k[j] - origin) >> shift) & dmask;
 				const uint32_t pk = bins[MSB64_BIN_SLOT(d)];
-				const uint32_t base = pk & 0xffffu, cnt = pk >> 16;
-				if (!resolved && cnt > 1) skeys[base + rank[j]] = k[j];
-				rank[j] = (base + (resolved || cnt == 1 || cnt > LOCAL_RANK_MAX ? rank[j] : 0u))
-					  | (cnt << 13) | (min(rank[j], 63u) << 26);
-			}
-		}
-		__syncthreads();
-		// 3b. final slot = bin base + number of keys of the bin that go before this one
-#pragma unroll
-		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			if (i < size) {
-				const uint32_t base = rank[j] & 0x1fffu, cnt = (rank[j] >> 13) & 0x1fffu;
-				const uint32_t arrival = rank[j] >> 26;
-				uint32_t slot = base;                      // already final unless ...
-				if (!resolved && cnt > 1) {
-					if (cnt <= LOCAL_RANK_MAX) {
-						uint32_t before = 0;
-						for (uint32_t q = 0; q < cnt; ++q) {
-							const uint64_t other = skeys[base + q];
-							before += (other < k[j]) || (other == k[j] && q < arrival);
-						}
-						slot = base + before;
-					} else if (arrival == 0) {
-						big[atomicAdd(&s_nbig, 1u)] = (base) | (cnt << 16);
-					}
+				const uint32_t p = (pk & 0xffffu) + rank[j];
+				skeys[p] = k[j];
+				srids[p] = r[j];
+				if (!resolved && rank[j] == 0 && pk >= (2u << 16)) {
+					if ((pk >> 16) <= LOCAL_SERIAL_MAX) list[atomicAdd(&s_nlist, 1u)] = pk;
+					else big[atomicAdd(&s_nbig, 1u)] = pk;
 				}
-				rank[j] = slot;
 			}
 		}
 		__syncthreads();
-		// 4a. final slots
-#pragma unroll
-		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			if (i < size) {
-				skeys[rank[j]] = k[j];
-				srids[rank[j]] = r[j];
+		// 3b. one thread per short colliding bin: insertion sort in place
+		const uint32_t nlist = s_nlist, nbig = s_nbig;     // read before the next barrier: thread 0 resets them for the next unit after it
+		for (uint32_t q = tid; q < nlist; q += THREADS) {
+			const uint32_t pk = list[q];
+			uint64_t *bk = skeys + (pk & 0xffffu), *br = srids + (pk & 0xffffu);
+			const uint32_t cnt = pk >> 16;
+			for (uint32_t i = 1; i < cnt; ++i) {
+				const uint64_t key = bk[i];
+				uint32_t at = i;
+				uint64_t prev = bk[at - 1];
+				if (prev <= key) continue;
+				const uint64_t rid = br[i];
+				do {
+					bk[at] = prev;
+					br[at] = br[at - 1];
+					--at;
+					if (at == 0) break;
+					prev = bk[at - 1];
+				} while (prev > key);
+				bk[at] = key;
+				br[at] = rid;
 			}
 		}
 		__syncthreads();
-		const uint32_t nbig = s_nbig;
 		for (uint32_t q = 0; q < nbig; ++q) {
 			const uint32_t pk = big[q];
 			block_bitonic(skeys + (pk & 0xffffu), srids + (pk & 0xffffu), pk >> 16);
 		}
 
-		// 4b. home
+		// 4. home (the next unit's first barrier orders these reads before its stores)
 		for (uint32_t i = tid; i < size; i += THREADS) {
 			st_stream_u64(dst_keys + i, skeys[i]);
 			st_stream_u64(dst_rids + i, srids[i]);
 		}
-		__syncthreads();
 #undef MSB64_BIN_SLOT
 	}
 }

@@ -103,9 +103,10 @@ __device__ __forceinline__ void emit_copy(const Ctx &c, Control *ctl, uint32_t b
 	}
 }
 
-// bits: digit width of this level; next_bits: of the next level (0 = this is the last).
+// bits: digit width of this level; next_bits: of the next level (0 = this is the last);
+// shift: position of this level's digit in the key.
 __global__ void __launch_bounds__(PLAN_THREADS)
-plan_kernel(const Ctx c, const int level, const int bits, const int next_bits)
+plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, const int shift)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t warps_per_block = PLAN_THREADS / 32;
@@ -144,7 +145,7 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits)
 
 		// pass 2: cursors, children
 		uint32_t base = s.begin;
-		uint32_t run_beg = 0, run_size = 0, local_pairs = 0;      // warp-uniform merge state
+		uint32_t run_beg = 0, run_size = 0, run_dig = 0, local_pairs = 0;   // warp-uniform merge state
 		for (uint32_t b0 = 0; b0 < NB; b0 += 32) {
 			const uint32_t b = b0 + lane;
 			const uint32_t cnt = b < NB ? h[b] : 0;
@@ -173,21 +174,24 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits)
 				if (cb > LOCAL_CAP || run_size + cb > LOCAL_CAP) {
 					if (run_size && lane == 0) {
 						const uint32_t u = atomicAdd(&ctl->nunits, 1u);
-						if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, 0u};
+						if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, unit_origin(shift, run_dig)};
 						else atomicOr(&ctl->error, 4u);
 					}
 					local_pairs += run_size;
 					run_size = 0;
 					if (cb > LOCAL_CAP) continue;
 				}
-				if (run_size == 0) run_beg = bb;
+				if (run_size == 0) {
+					run_beg = bb;
+					run_dig = b0 + src;
+				}
 				run_size += cb;
 			}
 		}
 		if (!last) {
 			if (run_size && lane == 0) {
 				const uint32_t u = atomicAdd(&ctl->nunits, 1u);
-				if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, 0u};
+				if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, unit_origin(shift, run_dig)};
 				else atomicOr(&ctl->error, 4u);
 			}
 			local_pairs += run_size;
