@@ -71,7 +71,7 @@ local_sort_kernel(const Ctx c)
 	uint32_t *big = list + LOCAL_LIST_MAX;                           // long bins:           base | size << 16
 	uint32_t *scratch = big + LOCAL_BIG_MAX;                         // [64]
 	uint64_t *wred = reinterpret_cast<uint64_t *>(scratch + 64);     // [2 * WARPS] OR, AND per warp
-	__shared__ uint32_t s_nlist, s_nbig;
+	__shared__ uint32_t s_nbig;
 
 	const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
 	const uint32_t nunits = min(c.ctl->nunits, c.max_units);
@@ -83,33 +83,33 @@ local_sort_kernel(const Ctx c)
 		uint64_t *dst_keys = c.keys[0] + un.begin, *dst_rids = c.rids[0] + un.begin;
 		const uint32_t size = un.size;
 
-		// 1. load (slots past the end re-read the last pair: no branches, and harmless
-		//    for the OR / AND reductions); which bits differ?
+		// 1. load.  Rows (THREADS consecutive slots) past the unit's end are skipped with
+		//    block-uniform branches; the slots of the last row past the end re-read the
+		//    last pair (no divergence, and harmless for the OR / AND reductions).
+		const uint32_t rows = (size + THREADS - 1) / THREADS;
 		uint64_t k[ITEMS], r[ITEMS];
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j)
-			k[j] = ld_stream_u64(src_keys + min(uint32_t(j * THREADS) + tid, size - 1));
+			if (j < rows) k[j] = ld_stream_u64(src_keys + min(uint32_t(j * THREADS) + tid, size - 1));
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j)
-			r[j] = ld_stream_u64(src_rids + min(uint32_t(j * THREADS) + tid, size - 1));
+			if (j < rows) r[j] = ld_stream_u64(src_rids + min(uint32_t(j * THREADS) + tid, size - 1));
 		// the bin table is free here (the previous unit is done with it)
 		{
 			uint4 *b4 = reinterpret_cast<uint4 *>(bins);
 			for (uint32_t i = tid; i < (LOCAL_NBINS + 32) / 4; i += THREADS)
 				b4[i] = make_uint4(0u, 0u, 0u, 0u);
 		}
-		if (tid == 0) {
-			s_nlist = 0;
-			s_nbig = 0;
-		}
+		if (tid == 0) s_nbig = 0;
 		// binning value: key minus the unit's origin (monotone; see unit_origin)
 		const uint64_t origin = unit_origin_key(un.origin);
 		uint64_t vor = k[0] - origin, vand = vor;
 #pragma unroll
-		for (int j = 1; j < ITEMS; ++j) {
-			vor |= k[j] - origin;
-			vand &= k[j] - origin;
-		}
+		for (int j = 1; j < ITEMS; ++j)
+			if (j < rows) {
+				vor |= k[j] - origin;
+				vand &= k[j] - origin;
+			}
 		{
 			const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(vor));
 			const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(vor >> 32));
@@ -121,14 +121,17 @@ local_sort_kernel(const Ctx c)
 			}
 		}
 		__syncthreads();
-		vor = 0;
-		vand = ~0ull;
-#pragma unroll
-		for (int w = 0; w < WARPS; ++w) {
-			vor |= wred[w];
-			vand &= wred[WARPS + w];
+		uint64_t diff;
+		{
+			static_assert(WARPS <= 32, "one lane per warp result");
+			const uint64_t o = lane < WARPS ? wred[lane] : 0ull;
+			const uint64_t a = lane < WARPS ? wred[WARPS + lane] : ~0ull;
+			const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(o));
+			const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(o >> 32));
+			const uint32_t alo = __reduce_and_sync(0xffffffffu, uint32_t(a));
+			const uint32_t ahi = __reduce_and_sync(0xffffffffu, uint32_t(a >> 32));
+			diff = ((uint64_t(ohi) << 32) | olo) & ~((uint64_t(ahi) << 32) | alo);
 		}
-		const uint64_t diff = vor & ~vand;
 
 		if (diff == 0) {
 			// all keys equal: nothing to order, only bring the pairs home
@@ -153,77 +156,82 @@ local_sort_kernel(const Ctx c)
 		b = min(b, top + 1);
 		const int shift = top + 1 - b;
 		const uint32_t nb = 1u << b, dmask = nb - 1;
-		// thread t owns the `per` consecutive digits t*per .. t*per+per-1 (per = 4 or 8) and
-		// keeps them as 16-byte chunks at chunk index c*THREADS + t: the scan reads them
-		// with conflict-free 16-byte loads
-		const int lper = max(b - 9, 2);
-		const uint32_t pmask = (1u << lper) - 1;
-#define MSB64_BIN_SLOT(d) ((((((d) & pmask) >> 2) * THREADS + ((d) >> lper)) << 2) | ((d) & 3u))
+		// thread t owns the 8 consecutive digits 8t .. 8t+7 and keeps them as two 16-byte
+		// chunks at chunk indices t and THREADS + t: the scan reads and writes them with
+		// conflict-free 16-byte accesses
+#define MSB64_BIN_SLOT(d) ((((d) & 4u) << 9) | (((d) >> 3) << 2) | ((d) & 3u))
+		static_assert(LOCAL_NBINS == 8 * THREADS, "two chunks of four bins per thread");
 		// do the digit bits cover every differing bit?  then equal digit = equal key
 		const bool resolved = (diff & ((1ull << shift) - 1)) == 0;
 
-		// branch-free (see tile_ranks in msb64_scatter.cuh): slots past the unit's end count
-		// into per-lane dummy bins behind the table
+		// branch-free inside a row (see tile_ranks in msb64_scatter.cuh): slots past the
+		// unit's end count into per-lane dummy bins behind the table
 		uint32_t rank[ITEMS];
 		uint32_t *dummy = bins + LOCAL_NBINS + lane;
 #pragma unroll
-		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			const uint32_t d = uint32_t((k[j] - origin) >> shift) & dmask;
-			uint32_t *slot = i < size ? &bins[MSB64_BIN_SLOT(d)] : dummy;
-			rank[j] = atomicAdd(slot, 1u);
-		}
+		for (int j = 0; j < ITEMS; ++j)
+			if (j < rows) {
+				const uint32_t i = j * THREADS + tid;
+				const uint32_t d = uint32_t((k[j] - origin) >> shift) & dmask;
+				uint32_t *slot = i < size ? &bins[MSB64_BIN_SLOT(d)] : dummy;
+				rank[j] = atomicAdd(slot, 1u);
+			}
 		__syncthreads();
-		// exclusive scan over bins in digit order; every bin becomes base | count << 16
+		// exclusive scan over bins in digit order; every bin becomes base | count << 16.
+		// The same scan numbers the bins that hold 2..LOCAL_SERIAL_MAX keys (count of those
+		// in the upper half of the scanned word): they are filed in `list` without atomics.
+		uint32_t nlist;
 		{
 			uint4 *b4 = reinterpret_cast<uint4 *>(bins);
-			const bool own = (tid << lper) < nb;
-			const bool two = lper == 3;
+			const bool own = (tid << 3) < nb;
 			uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
 			if (own) {
 				v0 = b4[tid];
-				if (two) v1 = b4[THREADS + tid];
+				v1 = b4[THREADS + tid];
 			}
-			const uint32_t sum = v0.x + v0.y + v0.z + v0.w + v1.x + v1.y + v1.z + v1.w;
+			const uint32_t cn[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+			uint32_t sum = 0;
+#pragma unroll
+			for (int q = 0; q < 8; ++q) {
+				sum += cn[q];
+				if (!resolved && cn[q] - 2u <= LOCAL_SERIAL_MAX - 2u) sum += 1u << 16;
+			}
 			uint32_t total;
-			uint32_t base = block_exclusive_scan<THREADS>(sum, scratch, &total);
+			const uint32_t ex = block_exclusive_scan<THREADS>(sum, scratch, &total);
+			nlist = total >> 16;
 			if (own) {
-				uint4 o;
-				o.x = base | (v0.x << 16); base += v0.x;
-				o.y = base | (v0.y << 16); base += v0.y;
-				o.z = base | (v0.z << 16); base += v0.z;
-				o.w = base | (v0.w << 16); base += v0.w;
-				b4[tid] = o;
-				if (two) {
-					o.x = base | (v1.x << 16); base += v1.x;
-					o.y = base | (v1.y << 16); base += v1.y;
-					o.z = base | (v1.z << 16); base += v1.z;
-					o.w = base | (v1.w << 16);
-					b4[THREADS + tid] = o;
+				uint32_t base = ex & 0xffffu, at = ex >> 16;
+				uint32_t o[8];
+#pragma unroll
+				for (int q = 0; q < 8; ++q) {
+					o[q] = base | (cn[q] << 16);
+					base += cn[q];
+					if (!resolved && cn[q] >= 2u) {
+						if (cn[q] <= LOCAL_SERIAL_MAX) list[at++] = o[q];
+						else big[atomicAdd(&s_nbig, 1u)] = o[q];
+					}
 				}
+				b4[tid] = make_uint4(o[0], o[1], o[2], o[3]);
+				b4[THREADS + tid] = make_uint4(o[4], o[5], o[6], o[7]);
 			}
 		}
 		__syncthreads();
 
-		// 3a. every pair to bin base + arrival rank; first arrivals file bins that need ordering
+		// 3a. every pair to bin base + arrival rank
 #pragma unroll
-		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			if (i < size) {
-				const uint32_t d = uint32_t((k[j] - origin) >> shift) & dmask;
-				const uint32_t pk = bins[MSB64_BIN_SLOT(d)];
-				const uint32_t p = (pk & 0xffffu) + rank[j];
-				skeys[p] = k[j];
-				srids[p] = r[j];
-				if (!resolved && rank[j] == 0 && pk >= (2u << 16)) {
-					if ((pk >> 16) <= LOCAL_SERIAL_MAX) list[atomicAdd(&s_nlist, 1u)] = pk;
-					else big[atomicAdd(&s_nbig, 1u)] = pk;
+		for (int j = 0; j < ITEMS; ++j)
+			if (j < rows) {
+				const uint32_t i = j * THREADS + tid;
+				if (i < size) {
+					const uint32_t d = uint32_t((k[j] - origin) >> shift) & dmask;
+					const uint32_t p = (bins[MSB64_BIN_SLOT(d)] & 0xffffu) + rank[j];
+					skeys[p] = k[j];
+					srids[p] = r[j];
 				}
 			}
-		}
 		__syncthreads();
 		// 3b. one thread per short colliding bin: insertion sort in place
-		const uint32_t nlist = s_nlist, nbig = s_nbig;     // read before the next barrier: thread 0 resets them for the next unit after it
+		const uint32_t nbig = s_nbig;     // read before the next barrier: thread 0 resets it for the next unit after it
 		for (uint32_t q = tid; q < nlist; q += THREADS) {
 			const uint32_t pk = list[q];
 			uint64_t *bk = skeys + (pk & 0xffffu), *br = srids + (pk & 0xffffu);

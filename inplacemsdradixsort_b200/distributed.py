@@ -1,0 +1,211 @@
+"""Sort sharded over several B200s: one process per GPU, range partition by key, local sort.
+
+The role of the reference's cross-NUMA-node phase (sample -> range histogram ->
+partition into per-node ranges -> every thread sorts its range; msb_64.c:1546-1606,
+1674-2198), re-thought for GPUs connected by NVLink/NVSwitch:
+
+    1. every rank histograms the top `bits` bits of its keys         (device kernel)
+    2. the histograms are all-gathered                                (NCCL)
+    3. every rank cuts the bin axis into `world` contiguous ranges of near-equal
+       global count -- all ranks compute the same cut from the same data, so no
+       further agreement step is needed; the same table gives every send and
+       receive count, no count exchange                              (host, tiny)
+    4. the local pairs are grouped by destination rank               (device kernel)
+    5. keys and rids are exchanged                                    (NCCL all-to-all,
+       i.e. grouped ncclSend/ncclRecv over NVLink)
+    6. every rank sorts what it received with the single-GPU sort     (device kernels)
+
+Afterwards rank r holds the r-th key range in ascending order and every key of rank r
+is <= every key of rank r+1 (the contract of the reference's sort() across NUMA
+nodes, msb_64.c:2180, include/msb_64.h:36).  Like the reference, the partition has a
+capacity factor (`fudge`): a rank that would receive more than capacity * fudge pairs
+raises Msb64Error(CAPACITY) where the reference's assert fires (msb_64.c:1574-1578).
+
+The device steps go through the C ABI (include/msb64_b200.h, section 4) and there is
+no CPU implementation of them in this package.  `ops` exists so that the host logic
+above (steps 2, 3, 5 and the bookkeeping) can be exercised by multi-process tests on
+the gloo backend with stand-in device steps supplied by the test suite.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import msb64 as _m
+
+DEFAULT_BITS = 12
+
+
+# --------------------------------------------------------------------- host logic
+def choose_ranges(global_hist: np.ndarray, world: int) -> np.ndarray:
+    """bin -> destination rank: `world` contiguous bin ranges of near-equal count.
+
+    A bin goes to the rank into whose share its midpoint falls; every rank computes
+    this from the same all-gathered histogram and gets the same table.  Bins are never
+    split (equal keys never straddle ranks, msb_64.c:1596-1606)."""
+    h = np.asarray(global_hist, dtype=np.uint64).astype(np.float64)
+    total = float(h.sum())
+    if total == 0 or world == 1:
+        return np.zeros(h.size, dtype=np.uint8)
+    mid = np.cumsum(h) - h / 2.0
+    dest = np.minimum((mid * world / total).astype(np.int64), world - 1)
+    return np.maximum.accumulate(dest).astype(np.uint8)       # monotone by construction; keep it exact
+
+
+def exchange_counts(hists: np.ndarray, table: np.ndarray, world: int) -> np.ndarray:
+    """counts[src][dst] = pairs rank `src` sends to rank `dst` under `table`."""
+    counts = np.zeros((world, world), dtype=np.int64)
+    for dst in range(world):
+        sel = table == dst
+        if sel.any():
+            counts[:, dst] = hists[:, sel].sum(axis=1)
+    return counts
+
+
+# --------------------------------------------------------------------- device steps
+class CudaOps:
+    """The device steps on torch CUDA tensors through libmsb64_b200.so."""
+
+    def __init__(self, device):
+        import torch
+        self.torch = torch
+        self.device = device
+        self.lib = _m.load_library()
+        if not torch.cuda.is_available() or _m.device_count() < 1:
+            raise _m.Msb64Error(-1, "ShardedSorter needs a CUDA device; there is no CPU path")
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def empty(self, count, dtype=None):
+        return self.torch.empty(int(count), dtype=dtype or self.torch.int64, device=self.device)
+
+    def from_numpy(self, a):
+        return self.torch.from_numpy(a).to(self.device, non_blocking=False)
+
+    def workspace(self, cap):
+        nbytes = _m.workspace_bytes(cap)
+        return self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device), nbytes
+
+    def digit_histogram(self, keys, n, shift, bits, out):
+        _m._raise(self.lib.msb64_b200_digit_histogram(keys.data_ptr(), n, shift, bits,
+                                                      out.data_ptr(), self._stream()))
+
+    def route(self, keys, rids, n, shift, bits, table, world, cursors, out_keys, out_rids):
+        _m._raise(self.lib.msb64_b200_route(keys.data_ptr(), rids.data_ptr(), n, shift, bits,
+                                            table.data_ptr(), world, cursors.data_ptr(),
+                                            out_keys.data_ptr(), out_rids.data_ptr(), self._stream()))
+
+    def sort(self, keys, rids, n, ws, ws_bytes):
+        _m._raise(self.lib.msb64_b200_sort_device(keys.data_ptr(), rids.data_ptr(), n, ws.data_ptr(),
+                                                  ws_bytes, self._stream(), None))
+
+
+# --------------------------------------------------------------------- the sorter
+class ShardedSorter:
+    """Reusable buffers + the six steps above for `capacity` local pairs per rank."""
+
+    def __init__(self, capacity: int, device=None, fudge: float = 1.125, bits: int = DEFAULT_BITS,
+                 group=None, ops=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 64:
+            raise _m.Msb64Error(-2, "at most 64 ranks (msb64_b200_route destinations)")
+        self.bits = int(bits)
+        self.shift = 64 - self.bits
+        self.capacity = int(capacity)
+        self.fudge = float(fudge)
+        if not (self.fudge >= 1.0):
+            raise _m.Msb64Error(-2, "fudge must be >= 1.0")
+        self.recv_cap = int(self.capacity * self.fudge) + 2
+        if self.recv_cap > _m.MSB64_MAX_PAIRS:
+            raise _m.Msb64Error(-3, "more than MSB64_MAX_PAIRS pairs per GPU")
+        self.ops = ops if ops is not None else CudaOps(device)
+        o = self.ops
+        self.hist = o.empty(1 << self.bits)
+        self.all_hist = o.empty(self.world << self.bits)
+        self.recv_keys = o.empty(self.recv_cap)
+        self.recv_rids = o.empty(self.recv_cap)
+        # the sort's scratch doubles as the send buffer: the exchange is over before the
+        # local sort starts, and the sort treats its workspace as uninitialised
+        self.ws, self.ws_bytes = o.workspace(self.recv_cap)
+        words = self.ws[: (self.ws.numel() // 8) * 8].view(torch.int64)
+        assert words.numel() >= 2 * self.capacity, "workspace smaller than the send buffers"
+        self.send_keys = words[: self.capacity]
+        self.send_rids = words[self.capacity: 2 * self.capacity]
+        self.last_counts = None
+
+    # -- steps 1-3
+    def plan(self, keys, n):
+        dist = self.dist
+        self.ops.digit_histogram(keys, n, self.shift, self.bits, self.hist)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.all_hist, self.hist, group=self.group)
+            hists = self.all_hist
+        else:
+            hists = self.hist
+        h = hists.cpu().numpy().reshape(self.world, 1 << self.bits)       # synchronises
+        table = choose_ranges(h.sum(axis=0), self.world)
+        counts = exchange_counts(h, table, self.world)
+        return table, counts
+
+    def sort(self, keys, rids, n: int | None = None):
+        """keys, rids: this rank's pairs (8-byte integer tensors on the sorter's device).
+        Returns (keys, rids, count) of this rank's key range, sorted; the tensors are
+        views of the sorter's receive buffers, valid until the next call."""
+        torch, dist = self.torch, self.dist
+        n = keys.numel() if n is None else int(n)
+        if n > self.capacity:
+            raise _m.Msb64Error(-2, f"{n} pairs exceed the sorter's capacity {self.capacity}")
+        table, counts = self.plan(keys, n)
+        self.last_counts = counts
+        send = counts[self.rank]
+        recv = counts[:, self.rank]
+        total = int(recv.sum())
+        if total > self.recv_cap:
+            raise _m.Msb64Error(-4, f"rank {self.rank} would receive {total} pairs, more than "
+                                    f"capacity * fudge = {self.recv_cap}")
+        if self.world == 1:
+            # nothing to exchange: the receive buffer gets the pairs, the sort runs on it
+            self.recv_keys[:n].copy_(keys[:n])
+            self.recv_rids[:n].copy_(rids[:n])
+        else:
+            starts = np.concatenate([[0], np.cumsum(send)[:-1]]).astype(np.uint32)
+            cursors = self.ops.from_numpy(starts.view(np.int32))
+            table_d = self.ops.from_numpy(table)
+            self.ops.route(keys, rids, n, self.shift, self.bits, table_d, self.world, cursors,
+                           self.send_keys, self.send_rids)
+            ins, outs = [int(x) for x in send], [int(x) for x in recv]
+            dist.all_to_all_single(self.recv_keys[:total], self.send_keys[:n], outs, ins, group=self.group)
+            dist.all_to_all_single(self.recv_rids[:total], self.send_rids[:n], outs, ins, group=self.group)
+        self.ops.sort(self.recv_keys, self.recv_rids, total, self.ws, self.ws_bytes)
+        return self.recv_keys[:total], self.recv_rids[:total], total
+
+    # -- acceptance across ranks (the cross-node half of check(), msb_64.c:2485-2495)
+    def boundaries_ordered(self, out_keys, out_n: int) -> bool:
+        """True on every rank iff every rank's last key <= the next non-empty rank's first."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return True
+        edge = torch.zeros(3, dtype=torch.int64, device=out_keys.device)
+        if out_n:
+            edge[0] = out_keys[0]
+            edge[1] = out_keys[out_n - 1]
+            edge[2] = 1
+        edges = torch.empty(3 * self.world, dtype=torch.int64, device=out_keys.device)
+        dist.all_gather_into_tensor(edges, edge, group=self.group)
+        e = edges.cpu().numpy().reshape(self.world, 3)
+        first, last = e[:, 0].view(np.uint64), e[:, 1].view(np.uint64)
+        prev = None
+        for r in range(self.world):
+            if not e[r, 2]:
+                continue
+            if prev is not None and first[r] < prev:
+                return False
+            prev = last[r]
+        return True
