@@ -139,6 +139,16 @@ class ShardedSorter:
         self.send_keys = words[: self.capacity]
         self.send_rids = words[self.capacity: 2 * self.capacity]
         self.last_counts = None
+        # every rank knows every rank's receive capacity, so that an overflow is raised on
+        # all ranks together (nobody is left waiting in the exchange)
+        caps = o.empty(self.world)
+        mine = o.empty(1)
+        mine.fill_(self.recv_cap)
+        if self.world > 1:
+            dist.all_gather_into_tensor(caps, mine, group=group)
+        else:
+            caps.copy_(mine)
+        self.recv_caps = caps.cpu().numpy().astype(np.int64)
 
     # -- steps 1-3
     def plan(self, keys, n):
@@ -167,9 +177,11 @@ class ShardedSorter:
         send = counts[self.rank]
         recv = counts[:, self.rank]
         total = int(recv.sum())
-        if total > self.recv_cap:
-            raise _m.Msb64Error(-4, f"rank {self.rank} would receive {total} pairs, more than "
-                                    f"capacity * fudge = {self.recv_cap}")
+        over = np.nonzero(counts.sum(axis=0) > self.recv_caps)[0]
+        if over.size:                                     # same verdict on every rank
+            r = int(over[0])
+            raise _m.Msb64Error(-4, f"rank {r} would receive {int(counts[:, r].sum())} pairs, more "
+                                    f"than its capacity * fudge = {int(self.recv_caps[r])}")
         if self.world == 1:
             # nothing to exchange: the receive buffer gets the pairs, the sort runs on it
             self.recv_keys[:n].copy_(keys[:n])

@@ -1,0 +1,148 @@
+"""The device steps of the multi-GPU range partition (include/msb64_b200.h section 4) and
+ShardedSorter on real GPUs: one GPU always, two GPUs over NCCL when the box has them."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from inputs import make  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(gpu, a):
+    d = gpu.DeviceArray(a.size)
+    if a.size:
+        d.upload(np.ascontiguousarray(a))
+    return d
+
+
+@pytest.mark.parametrize("kind", ["uniform", "low24", "skew", "sorted"])
+@pytest.mark.parametrize("n,bits,shift", [(0, 8, 56), (1, 12, 52), (100_003, 12, 52), (1 << 20, 10, 20),
+                                          (300_001, 1, 63)])
+def test_digit_histogram(gpu, kind, n, bits, shift):
+    lib = gpu.load_library()
+    keys = make(kind, n, seed=5)
+    dk = _dev(gpu, keys)
+    dh = gpu.DeviceArray(1 << bits)
+    assert lib.msb64_b200_digit_histogram(dk.ptr, n, shift, bits, dh.ptr, None) == 0
+    got = dh.download()
+    want = np.bincount(((keys >> np.uint64(shift)) & np.uint64((1 << bits) - 1)).astype(np.int64),
+                       minlength=1 << bits).astype(np.uint64)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "skew", "dup16", "sorted"])
+@pytest.mark.parametrize("n,ndest", [(1, 2), (4097, 3), (100_003, 8), (1 << 20, 64), (300_001, 1)])
+def test_route_groups_by_destination(gpu, kind, n, ndest):
+    lib = gpu.load_library()
+    bits, shift = 12, 52
+    keys = make(kind, n, seed=9)
+    rids = np.arange(n, dtype=np.uint64) * np.uint64(7) + np.uint64(1)
+    digit = ((keys >> np.uint64(shift)) & np.uint64((1 << bits) - 1)).astype(np.int64)
+    table = (np.arange(1 << bits) * ndest // (1 << bits)).astype(np.uint8)      # contiguous bin ranges
+    dest = table[digit]
+    counts = np.bincount(dest, minlength=ndest)
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.uint32)
+    dk, dr = _dev(gpu, keys), _dev(gpu, rids)
+    ok_, or_ = gpu.DeviceArray(n), gpu.DeviceArray(n)
+    dt = gpu.DeviceArray((table.size + 7) // 8)
+    lib.msb64_b200_memcpy_h2d(dt.ptr, table.ctypes.data, table.size, None)
+    dc = gpu.DeviceArray((ndest + 1) // 2 + 1)
+    lib.msb64_b200_memcpy_h2d(dc.ptr, starts.ctypes.data, starts.size * 4, None)
+    lib.msb64_b200_stream_sync(None)
+    assert lib.msb64_b200_route(dk.ptr, dr.ptr, n, shift, bits, dt.ptr, ndest, dc.ptr, ok_.ptr, or_.ptr, None) == 0
+    gk, gr = ok_.download(), or_.download()
+    cur = np.zeros(dc.count, dtype=np.uint64)
+    dc.download(cur)
+    ends = cur.view(np.uint32)[:ndest]
+    assert np.array_equal(ends.astype(np.int64), (starts + counts).astype(np.int64)), "cursors not advanced by the counts"
+    for d in range(ndest):
+        lo, hi = int(starts[d]), int(starts[d] + counts[d])
+        sel = dest == d
+        want = np.lexsort((rids[sel], keys[sel]))
+        got = np.lexsort((gr[lo:hi], gk[lo:hi]))
+        assert np.array_equal(gk[lo:hi][got], keys[sel][want]), f"destination {d}: keys differ"
+        assert np.array_equal(gr[lo:hi][got], rids[sel][want]), f"destination {d}: rids differ"
+
+
+@pytest.mark.parametrize("kind", ["uniform", "low24", "dup16"])
+def test_sharded_sorter_single_gpu(gpu, oracle, kind):
+    import torch
+    from inplacemsdradixsort_b200.distributed import ShardedSorter
+    n = 200_003
+    keys = make(kind, n, seed=3)
+    rids = np.arange(n, dtype=np.uint64)
+    dev = torch.device("cuda", 0)
+    s = ShardedSorter(n, dev)
+    kt = torch.from_numpy(keys.view(np.int64)).to(dev)
+    rt = torch.from_numpy(rids.view(np.int64)).to(dev)
+    ok_, or_, cnt = s.sort(kt, rt)
+    torch.cuda.synchronize()
+    assert cnt == n
+    gk = ok_.cpu().numpy().view(np.uint64)
+    gr = or_.cpu().numpy().view(np.uint64)
+    wk = np.concatenate([keys, np.zeros(n // 2 + 64, np.uint64)])
+    wr = np.concatenate([rids, np.zeros(n // 2 + 64, np.uint64)])
+    oracle.sort([wk], [wr], [n])
+    assert np.array_equal(gk, wk[:n])
+    assert np.array_equal(gr[np.lexsort((gr, gk))], wr[:n][np.lexsort((wr[:n], wk[:n]))])
+    assert s.boundaries_ordered(ok_, cnt)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, kind, n, result):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from inplacemsdradixsort_b200.distributed import ShardedSorter
+        n_local = n + 1000 * rank
+        keys = make(kind, n_local, seed=40 + rank)
+        rids = np.arange(n_local, dtype=np.uint64) + np.uint64(rank << 40)
+        s = ShardedSorter(n_local, dev, fudge=1.3)
+        ok_, or_, cnt = s.sort(torch.from_numpy(keys.view(np.int64)).to(dev),
+                               torch.from_numpy(rids.view(np.int64)).to(dev))
+        ordered = s.boundaries_ordered(ok_, cnt)
+        torch.cuda.synchronize()
+        result[rank] = (ok_.cpu().numpy().view(np.uint64).copy(), or_.cpu().numpy().view(np.uint64).copy(),
+                        keys, rids, ordered)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "sorted"])
+def test_sharded_sorter_two_gpus_nccl(gpu, kind):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("box has one GPU; the 2-rank path is covered on CPU by test_distributed_gloo.py")
+    world = 2
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_nccl_worker, args=(world, _free_port(), kind, 1_000_003, result), nprocs=world, join=True)
+    res = [result[r] for r in range(world)]
+    all_k = np.concatenate([r[2] for r in res])
+    all_r = np.concatenate([r[3] for r in res])
+    out_k = np.concatenate([r[0] for r in res])
+    out_r = np.concatenate([r[1] for r in res])
+    order = np.lexsort((all_r, all_k))
+    assert np.array_equal(out_k, all_k[order])
+    assert np.array_equal(out_r[np.lexsort((out_r, out_k))], all_r[order])
+    assert all(r[4] for r in res)
