@@ -35,7 +35,7 @@ using namespace msb64;
 #define MSB64_SCATTER_THREADS 256
 #endif
 #ifndef MSB64_SCATTER_MINB
-#define MSB64_SCATTER_MINB 2
+#define MSB64_SCATTER_MINB 3
 #endif
 constexpr int SCATTER_THREADS = MSB64_SCATTER_THREADS;
 constexpr int SCATTER_MINB = MSB64_SCATTER_MINB;

@@ -7,20 +7,25 @@
 // buffer to the other and the last pass / the local sort lands it in the caller's
 // arrays.  Algorithmic traffic: 32 bytes per pair (16 read + 16 written).
 //
-// Per tile of TILE pairs:
-//   1. 16-byte coalesced loads of the keys into registers;
-//   2. rank of every key among the tile's keys with the same digit: one shared-memory
+// A block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Per tile of TILE pairs:
+//   0. keys and rids of the tile land in shared memory by two bulk asynchronous copies
+//      (cp.async.bulk + mbarrier, the non-tensor TMA path) issued by one thread: no
+//      register is tied up by a load in flight, so three blocks fit on an SM and cover
+//      one another's load latency; tile descriptors are read two tiles ahead;
+//   1. rank of every key among the tile's keys with the same digit: one shared-memory
 //      atomicAdd on the tile's bin counter (B200 sustains ~9 spread shared atomics
 //      per clock per SM, tools/microbench.cu; a ballot multisplit manages ~1); a warp
-//      whose digits are all equal takes a single atomic; a block scan over the
-//      bin counts turns the ranks into positions in the tile's bin-sorted order;
-//   3. one global atomicAdd per non-empty bin on the segment's write cursor
+//      whose digits are all equal takes a single atomic;
+//   2. one global atomicAdd per non-empty bin on the segment's write cursor
 //      reserves the tile's slice of that bin (the cursors were initialised by the
-//      plan kernel from the histogram).  MSD radix sort is not stable, so the
-//      order in which tiles claim their slices is free and no block ever waits
+//      plan kernel from the histogram); a block scan over the bin counts gives the
+//      bins' positions in the tile's bin-sorted order.  MSD radix sort is not stable,
+//      so the order in which tiles claim their slices is free and no block ever waits
 //      for another one;
-//   4. keys and rids are staged through shared memory in bin order and written
-//      out so that consecutive lanes write consecutive addresses.
+//   3. the pairs do not move inside shared memory: only a 2-byte source slot per pair
+//      is written in bin order (sidx[position] = slot);
+//   4. write-out: position i gathers key and rid of slot sidx[i] and stores them to
+//      delta[bin] + i, so that consecutive lanes write consecutive addresses.
 #pragma once
 #include "msb64_common.cuh"
 
@@ -31,26 +36,69 @@ struct ScatterCfg {
 	static constexpr int NB = 1 << BITS;
 	static constexpr int ITEMS = TILE / THREADS;
 	static constexpr int BPT = (NB + THREADS - 1) / THREADS;   // bins per thread
-	static constexpr size_t SMEM = size_t(TILE) * 16               // staged keys + rids
+	static constexpr size_t SMEM = size_t(TILE) * 16               // keys + rids of the tile (bulk-copied)
+				       + size_t(TILE) * 2              // source slot of every bin-ordered position
 				       + size_t(NB + 32) * 4           // tile-bin counters / bases (+ dummies)
 				       + size_t(NB) * 4                // delta
-				       + 64 * 4;                       // scan scratch
+				       + 64 * 4                        // scan scratch
+				       + 3 * 32                        // tile descriptors, three deep
+				       + 16;                           // mbarrier
 };
+
+// What a block needs to know about one tile (kept in shared memory, written by thread 0).
+struct TileDesc {
+	uint32_t seg;     // index of the segment (row of the cursor table)
+	uint32_t begin;   // the segment's first element
+	uint32_t end;     // one past its last
+	uint32_t lo;      // first element slot of the tile (even)
+	uint32_t flags;   // bit 0: source buffer, bit 1: segment skipped, bit 2: no such tile
+	uint32_t pad[3];
+};
+constexpr uint32_t TD_BUF = 1u, TD_SKIP = 2u, TD_NONE = 4u;
+
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		     :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+			     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			     "selp.u32 %0, 1, 0, p;\n\t}"
+			     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+	} while (!done);
+}
+// bytes: multiple of 16; dst and src 16-byte aligned
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		     :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
 
 // Rank of a key among the tile's keys with the same digit = old value of the tile's
 // bin counter.  The hot loop is branch-free on purpose: ptxas re-materialises the
 // shared-window base (S2UR SR_CgaCtaId) in front of every ATOMS that sits behind a
 // branch, which made the XU pipe the bottleneck.  A warp whose ITEMS x 32 digits are
 // all equal (low-entropy input) claims its ranks with one atomic instead.
+// Result per item: rank | digit << 13 (digits NB.. are the dummy bins of invalid items).
+constexpr uint32_t RANK_BITS = 13, RANK_MASK = (1u << RANK_BITS) - 1;
 template <int ITEMS, int NB>
-__device__ __forceinline__ void tile_ranks(uint32_t *cnt, const uint64_t (&k)[ITEMS], int shift,
-					   uint32_t validmask, uint32_t (&rank)[ITEMS])
+__device__ __forceinline__ void tile_ranks(uint32_t *cnt, uint32_t (&d)[ITEMS])
 {
-	// items outside the segment count into a per-lane dummy bin behind the real ones
-	uint32_t d[ITEMS];
-#pragma unroll
-	for (int j = 0; j < ITEMS; ++j)
-		d[j] = ((validmask >> j) & 1u) ? (uint32_t(k[j] >> shift) & (NB - 1)) : NB + lane_id();
 	const uint32_t d0 = __shfl_sync(0xffffffffu, d[0], 0);
 	bool same = true;
 #pragma unroll
@@ -60,10 +108,10 @@ __device__ __forceinline__ void tile_ranks(uint32_t *cnt, const uint64_t (&k)[IT
 		if (lane_id() == 0) base = atomicAdd(&cnt[d0], uint32_t(32 * ITEMS));
 		base = __shfl_sync(0xffffffffu, base, 0);
 #pragma unroll
-		for (int j = 0; j < ITEMS; ++j) rank[j] = base + j * 32 + lane_id();
+		for (int j = 0; j < ITEMS; ++j) d[j] = (base + j * 32 + lane_id()) | (d0 << RANK_BITS);
 	} else {
 #pragma unroll
-		for (int j = 0; j < ITEMS; ++j) rank[j] = atomicAdd(&cnt[d[j]], 1u);
+		for (int j = 0; j < ITEMS; ++j) d[j] = atomicAdd(&cnt[d[j]], 1u) | (d[j] << RANK_BITS);
 	}
 }
 
@@ -73,83 +121,127 @@ scatter_kernel(const Ctx c, const int level, const int shift)
 {
 	using Cfg = ScatterCfg<BITS, THREADS>;
 	constexpr int NB = Cfg::NB, ITEMS = Cfg::ITEMS, BPT = Cfg::BPT;
-	static_assert(ITEMS % 2 == 0, "tile is loaded as 16-byte pairs");
+	static_assert(ITEMS % 2 == 0, "keys are read from shared memory as 16-byte pairs");
+	static_assert(TILE <= RANK_MASK + 1 && TILE <= 65536, "rank / slot packing");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	uint64_t *skeys = reinterpret_cast<uint64_t *>(smem_raw);       // [TILE]
-	uint64_t *srids = skeys + TILE;                                 // [TILE]
-	uint32_t *cnt = reinterpret_cast<uint32_t *>(srids + TILE);     // [NB] counts, then local bases
+	uint64_t *kin = reinterpret_cast<uint64_t *>(smem_raw);         // [TILE] keys of the tile
+	uint64_t *rin = kin + TILE;                                     // [TILE] rids of the tile
+	uint16_t *sidx = reinterpret_cast<uint16_t *>(rin + TILE);      // [TILE] source slot by bin-ordered position
+	uint32_t *cnt = reinterpret_cast<uint32_t *>(sidx + TILE);      // [NB + 32] counts, then local bases
 	uint32_t *delta = cnt + NB + 32;                                // [NB] global - local base
 	uint32_t *scratch = delta + NB;                                 // [64]
+	TileDesc *sdesc = reinterpret_cast<TileDesc *>(scratch + 64);   // [3]
+	uint64_t *bar = reinterpret_cast<uint64_t *>(sdesc + 3);
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ntiles = c.ctl->ntiles[level];
 	const Seg *segs = (level & 1) ? c.segs[1] : c.segs[0];
 	const Tile *tiles = (level & 1) ? c.tiles[1] : c.tiles[0];
 	uint32_t *cursors = (level & 1) ? c.hist[1] : c.hist[0];
+	const uint32_t G = gridDim.x;
+	if (blockIdx.x >= ntiles) return;
 
-	for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+	// thread 0 only: descriptor of tile t into slot
+	auto fetch_desc = [&](uint32_t t, TileDesc *slot) {
+		if (t >= ntiles) {
+			slot->flags = TD_NONE;
+			return;
+		}
 		const Tile tile = tiles[t];
 		const Seg s = segs[tile.seg];
-		if (s.skip) continue;
-		const uint64_t *src_keys = s.buf ? c.keys[1] : c.keys[0];
-		const uint64_t *src_rids = s.buf ? c.rids[1] : c.rids[0];
-		uint64_t *dst_keys = s.buf ? c.keys[0] : c.keys[1];
-		uint64_t *dst_rids = s.buf ? c.rids[0] : c.rids[1];
-		const uint32_t end = s.begin + s.size;
-		const uint32_t lo = seg_tile_origin(s.begin) + tile.idx * TILE;
-		const bool full = lo >= s.begin && lo + TILE <= end;
-		const uint32_t count = min(lo + TILE, end) - max(lo, s.begin);
+		slot->seg = tile.seg;
+		slot->begin = s.begin;
+		slot->end = s.begin + s.size;
+		slot->lo = seg_tile_origin(s.begin) + tile.idx * TILE;
+		slot->flags = (s.buf ? TD_BUF : 0u) | (s.skip ? TD_SKIP : 0u);
+	};
+	// thread 0 only: a tile whose whole window lies inside the array is fetched by bulk
+	// copies (slots outside the segment receive the neighbours' data and are ignored)
+	auto start_copy = [&](const TileDesc &d) {
+		if ((d.flags & (TD_SKIP | TD_NONE)) || d.lo + TILE > c.n) return;
+		const bool b = d.flags & TD_BUF;
+		mbar_expect_tx(bar, TILE * 16);
+		bulk_copy_g2s(kin, (b ? c.keys[1] : c.keys[0]) + d.lo, TILE * 8, bar);
+		bulk_copy_g2s(rin, (b ? c.rids[1] : c.rids[0]) + d.lo, TILE * 8, bar);
+	};
 
-		for (int i = tid; i < NB + 32; i += THREADS) cnt[i] = 0;
-		__syncthreads();
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		fetch_desc(blockIdx.x, &sdesc[0]);
+		fetch_desc(blockIdx.x + G, &sdesc[1]);
+		start_copy(sdesc[0]);
+	}
+	for (int i = tid; i < NB + 32; i += THREADS) cnt[i] = 0;
+	__syncthreads();
 
-		// 1. keys -> registers, 2. rank inside the tile's bin
-		uint64_t k[ITEMS];
-		uint32_t rank[ITEMS];
-		uint32_t validmask = 0;      // bit j: item j is inside the segment
-		if (full) {
-#pragma unroll
-			for (int j = 0; j < ITEMS / 2; ++j) {
-				const ulonglong2 v = ld_stream_u64x2(src_keys + lo + (j * THREADS + tid) * 2);
-				k[2 * j] = v.x;
-				k[2 * j + 1] = v.y;
+	uint32_t parity = 0, slot = 0;
+	for (uint32_t t = blockIdx.x; t < ntiles; t += G, slot = slot == 2 ? 0 : slot + 1) {
+		const TileDesc cur = sdesc[slot];
+		TileDesc *next_slot = &sdesc[slot == 2 ? 0 : slot + 1];
+		TileDesc *after_slot = &sdesc[slot == 0 ? 2 : slot - 1];       // slot + 2 mod 3
+		if (cur.flags & TD_SKIP) {
+			if (tid == 0) {
+				start_copy(*next_slot);
+				fetch_desc(t + 2 * G, after_slot);
 			}
-			validmask = (1u << ITEMS) - 1;
+			__syncthreads();
+			continue;
+		}
+		const bool src_b = cur.flags & TD_BUF;
+		uint64_t *dst_keys = src_b ? c.keys[0] : c.keys[1];
+		uint64_t *dst_rids = src_b ? c.rids[0] : c.rids[1];
+		const uint32_t lo = cur.lo;
+		const bool full = lo >= cur.begin && lo + TILE <= cur.end;
+		const uint32_t count = min(lo + TILE, cur.end) - max(lo, cur.begin);
+
+		// 0. the tile's pairs in shared memory
+		if (lo + TILE <= c.n) {
+			mbar_wait(bar, parity);
+			parity ^= 1u;
 		} else {
+			// the window crosses the end of the array (last tile only): plain loads
+			const uint64_t *src_keys = src_b ? c.keys[1] : c.keys[0];
+			const uint64_t *src_rids = src_b ? c.rids[1] : c.rids[0];
+			for (uint32_t i = tid; i < TILE; i += THREADS) {
+				const uint32_t e = lo + i;
+				if (e >= cur.begin && e < cur.end) {
+					kin[i] = ld_stream_u64(src_keys + e);
+					rin[i] = ld_stream_u64(src_rids + e);
+				}
+			}
+			__syncthreads();
+		}
+
+		// 1. digits, ranks inside the tile's bins.  Thread `tid` owns slots
+		//    (jj * THREADS + tid) * 2 + {0, 1}; items outside the segment count into a
+		//    per-lane dummy bin behind the real ones
+		uint32_t dr[ITEMS];
+		{
+			const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(kin);
 #pragma unroll
-			for (int j = 0; j < ITEMS; ++j) {
-				const uint32_t e = lo + ((j >> 1) * THREADS + tid) * 2 + (j & 1);
-				const bool valid = e >= s.begin && e < end;
-				k[j] = valid ? ld_stream_u64(src_keys + e) : 0;
-				validmask |= uint32_t(valid) << j;
+			for (int jj = 0; jj < ITEMS / 2; ++jj) {
+				const ulonglong2 v = k2[jj * THREADS + tid];
+				dr[2 * jj] = uint32_t(v.x >> shift) & (NB - 1);
+				dr[2 * jj + 1] = uint32_t(v.y >> shift) & (NB - 1);
+			}
+			if (!full) {
+#pragma unroll
+				for (int j = 0; j < ITEMS; ++j) {
+					const uint32_t e = lo + ((j >> 1) * THREADS + tid) * 2 + (j & 1);
+					if (e < cur.begin || e >= cur.end) dr[j] = NB + lane_id();
+				}
 			}
 		}
-		tile_ranks<ITEMS, NB>(cnt, k, shift, validmask, rank);
-		// rids: issued now, consumed after the scan
-		uint64_t r[ITEMS];
-		if (full) {
-#pragma unroll
-			for (int j = 0; j < ITEMS / 2; ++j) {
-				const ulonglong2 v = ld_stream_u64x2(src_rids + lo + (j * THREADS + tid) * 2);
-				r[2 * j] = v.x;
-				r[2 * j + 1] = v.y;
-			}
-		} else {
-#pragma unroll
-			for (int j = 0; j < ITEMS; ++j) {
-				const uint32_t e = lo + ((j >> 1) * THREADS + tid) * 2 + (j & 1);
-				r[j] = ((validmask >> j) & 1u) ? ld_stream_u64(src_rids + e) : 0;
-			}
-		}
+		tile_ranks<ITEMS, NB>(cnt, dr);
 		__syncthreads();
 
-		// 3. per bin: claim the tile's slice of the segment's bin, exclusive scan over bins
+		// 2. per bin: claim the tile's slice of the segment's bin, exclusive scan over bins
 		uint32_t tot[BPT], g[BPT], sum = 0;
 #pragma unroll
 		for (int q = 0; q < BPT; ++q) {
 			const int b = tid * BPT + q;
 			tot[q] = b < NB ? cnt[b] : 0;
-			g[q] = tot[q] ? atomicAdd(&cursors[size_t(tile.seg) * NB + b], tot[q]) : 0;
+			g[q] = tot[q] ? atomicAdd(&cursors[size_t(cur.seg) * NB + b], tot[q]) : 0;
 			sum += tot[q];
 		}
 		uint32_t total;
@@ -165,25 +257,31 @@ scatter_kernel(const Ctx c, const int level, const int shift)
 		}
 		__syncthreads();
 
-		// 4a. stage keys and rids in bin order
+		// 3. bin-ordered position -> source slot
 #pragma unroll
-		for (int j = 0; j < ITEMS; ++j)
-			if ((validmask >> j) & 1u) {
-				const uint32_t p = cnt[uint32_t(k[j] >> shift) & (NB - 1)] + rank[j];
-				skeys[p] = k[j];
-				srids[p] = r[j];
-			}
-		__syncthreads();
-
-		// 4b. coalesced write-out: slot i of the staged tile goes to delta[bin] + i
-		for (uint32_t i = tid; i < count; i += THREADS) {
-			const uint64_t key = skeys[i];
-			const uint32_t d = uint32_t(key >> shift) & (NB - 1);
-			const uint32_t dst = delta[d] + i;
-			st_stream_u64(dst_keys + dst, key);
-			st_stream_u64(dst_rids + dst, srids[i]);
+		for (int j = 0; j < ITEMS; ++j) {
+			const uint32_t d = dr[j] >> RANK_BITS;
+			if (d < NB) sidx[cnt[d] + (dr[j] & RANK_MASK)] = uint16_t(((j >> 1) * THREADS + tid) * 2 + (j & 1));
 		}
 		__syncthreads();
+
+		// 4. coalesced write-out: position i of the bin-ordered tile goes to delta[bin] + i
+#pragma unroll 4
+		for (uint32_t i = tid; i < count; i += THREADS) {
+			const uint32_t s = sidx[i];
+			const uint64_t key = kin[s];
+			const uint64_t rid = rin[s];
+			const uint32_t dst = delta[uint32_t(key >> shift) & (NB - 1)] + i;
+			st_stream_u64(dst_keys + dst, key);
+			st_stream_u64(dst_rids + dst, rid);
+		}
+		// meanwhile: counters back to zero for the next tile, descriptor of the tile after it
+		for (int i = tid; i < NB + 32; i += THREADS) cnt[i] = 0;
+		if (tid == 0) fetch_desc(t + 2 * G, after_slot);
+		__syncthreads();
+		// the tile's buffers are free: request the next tile (the other blocks on this SM
+		// cover the latency)
+		if (tid == 0) start_copy(*next_slot);
 	}
 }
 
