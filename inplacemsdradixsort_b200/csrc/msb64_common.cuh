@@ -23,7 +23,10 @@ namespace msb64 {
 
 constexpr int MAX_LEVELS = 16;          // digits per key (64 bits / >= 4 bits)
 constexpr int MAX_BITS = 11;            // widest digit a level may use
-constexpr uint32_t LOCAL_CAP = 4096;    // pairs the local sort holds in shared memory
+#ifndef MSB64_LOCAL_CAP
+#define MSB64_LOCAL_CAP 4096
+#endif
+constexpr uint32_t LOCAL_CAP = MSB64_LOCAL_CAP;   // pairs the local sort holds in shared memory
 constexpr uint32_t TILE = 4096;         // element slots per histogram/scatter tile
 constexpr uint32_t COPY_TILE = 8192;    // pairs per copy tile
 

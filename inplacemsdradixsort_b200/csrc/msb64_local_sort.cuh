@@ -23,9 +23,26 @@
 
 namespace msb64 {
 
-constexpr int LOCAL_THREADS = 512;
-constexpr int LOCAL_ITEMS = LOCAL_CAP / LOCAL_THREADS;
-constexpr int LOCAL_BITS = 12;                  // at most 4096 bins
+constexpr int LOCAL_ITEMS = 8;
+constexpr int LOCAL_THREADS = LOCAL_CAP / LOCAL_ITEMS;
+#ifndef MSB64_LOCAL_MINB
+#define MSB64_LOCAL_MINB 2
+#endif
+constexpr int LOCAL_MINB = MSB64_LOCAL_MINB;     // resident blocks per SM the register budget is cut for
+constexpr int LOCAL_OWNERS = LOCAL_THREADS >= 512 ? 512 : 256;   // threads that own bins in the scan
+constexpr int LOCAL_LOG_OWNERS = LOCAL_OWNERS == 512 ? 9 : 8;
+static_assert(LOCAL_THREADS % 32 == 0 && LOCAL_THREADS >= LOCAL_OWNERS && LOCAL_THREADS <= 1024, "block shape");
+#ifndef MSB64_LOCAL_BITS
+#define MSB64_LOCAL_BITS 12
+#endif
+constexpr int LOCAL_BITS = MSB64_LOCAL_BITS;    // at most 2^LOCAL_BITS bins
+#ifndef MSB64_LOCAL_EXTRA
+#define MSB64_LOCAL_EXTRA 0
+#endif
+constexpr int LOCAL_EXTRA_BITS = MSB64_LOCAL_EXTRA;   // bins per key: 2^EXTRA .. 2^(EXTRA+1)
+constexpr int LOCAL_LPER = LOCAL_BITS - LOCAL_LOG_OWNERS;      // log2(bins per thread): 8 or 16 bins, as chunks of 4
+constexpr int LOCAL_CHUNKS = (1 << LOCAL_LPER) / 4;
+static_assert(LOCAL_LPER >= 2 && LOCAL_LPER <= 5, "bin layout");
 constexpr uint32_t LOCAL_NBINS = 1u << LOCAL_BITS;
 constexpr uint32_t LOCAL_SERIAL_MAX = 16;       // bins up to this size: ordered by one thread
 constexpr uint32_t LOCAL_LIST_MAX = LOCAL_CAP / 2;                       // bins with >= 2 keys
@@ -58,11 +75,11 @@ __device__ __forceinline__ void block_bitonic(uint64_t *k, uint64_t *r, const ui
 	}
 }
 
-__global__ void __launch_bounds__(LOCAL_THREADS, 2)
+__global__ void __launch_bounds__(LOCAL_THREADS, LOCAL_MINB)
 local_sort_kernel(const Ctx c)
 {
 	constexpr int THREADS = LOCAL_THREADS, ITEMS = LOCAL_ITEMS, WARPS = THREADS / 32;
-	static_assert(THREADS == 512, "the bin layout assumes 512 threads");
+	constexpr int OWNERS = LOCAL_OWNERS;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint64_t *skeys = reinterpret_cast<uint64_t *>(smem_raw);        // [LOCAL_CAP]
 	uint64_t *srids = skeys + LOCAL_CAP;                             // [LOCAL_CAP]
@@ -76,24 +93,37 @@ local_sort_kernel(const Ctx c)
 	const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
 	const uint32_t nunits = min(c.ctl->nunits, c.max_units);
 
+	// The loop is software-pipelined: the pairs of the NEXT unit are requested from HBM as
+	// soon as the current unit's pairs have left the registers for shared memory (after step
+	// 3a), so that their latency hides behind steps 3b and 4.
+	uint64_t k[ITEMS], r[ITEMS];
+	// Rows (THREADS consecutive slots) past the unit's end are skipped with block-uniform
+	// branches; the slots of the last row past the end re-read the last pair (no
+	// divergence, and harmless for the OR / AND reductions).
+	auto load_unit = [&](const Unit &x) {
+		const uint64_t *src_keys = (x.buf ? c.keys[1] : c.keys[0]) + x.begin;
+		const uint64_t *src_rids = (x.buf ? c.rids[1] : c.rids[0]) + x.begin;
+		const uint32_t nrows = (x.size + THREADS - 1) / THREADS;
+#pragma unroll
+		for (int j = 0; j < ITEMS; ++j)
+			if (j < nrows) k[j] = ld_stream_u64(src_keys + min(uint32_t(j * THREADS) + tid, x.size - 1));
+#pragma unroll
+		for (int j = 0; j < ITEMS; ++j)
+			if (j < nrows) r[j] = ld_stream_u64(src_rids + min(uint32_t(j * THREADS) + tid, x.size - 1));
+	};
+	Unit next = Unit{0u, 1u, 0u, 0u};
+	if (blockIdx.x < nunits) {
+		next = c.units[blockIdx.x];
+		load_unit(next);
+	}
+
 	for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
-		const Unit un = c.units[u];
-		const uint64_t *src_keys = (un.buf ? c.keys[1] : c.keys[0]) + un.begin;
-		const uint64_t *src_rids = (un.buf ? c.rids[1] : c.rids[0]) + un.begin;
+		// 1. the unit's pairs are in (or on their way to) the registers
+		const Unit un = next;
+		const bool more = u + gridDim.x < nunits;
 		uint64_t *dst_keys = c.keys[0] + un.begin, *dst_rids = c.rids[0] + un.begin;
 		const uint32_t size = un.size;
-
-		// 1. load.  Rows (THREADS consecutive slots) past the unit's end are skipped with
-		//    block-uniform branches; the slots of the last row past the end re-read the
-		//    last pair (no divergence, and harmless for the OR / AND reductions).
 		const uint32_t rows = (size + THREADS - 1) / THREADS;
-		uint64_t k[ITEMS], r[ITEMS];
-#pragma unroll
-		for (int j = 0; j < ITEMS; ++j)
-			if (j < rows) k[j] = ld_stream_u64(src_keys + min(uint32_t(j * THREADS) + tid, size - 1));
-#pragma unroll
-		for (int j = 0; j < ITEMS; ++j)
-			if (j < rows) r[j] = ld_stream_u64(src_rids + min(uint32_t(j * THREADS) + tid, size - 1));
 		// the bin table is free here (the previous unit is done with it)
 		{
 			uint4 *b4 = reinterpret_cast<uint4 *>(bins);
@@ -146,21 +176,25 @@ local_sort_kernel(const Ctx c)
 				}
 			}
 			__syncthreads();
+			if (more) {
+				next = c.units[u + gridDim.x];
+				load_unit(next);
+			}
 			continue;
 		}
 
 		// 2. counting sort on the top differing bits, 1-2 bins per key
 		const int top = 63 - __clzll(diff);                      // highest differing bit
 		int b = 32 - __clz(size - 1);                            // ceil(log2(size)), size >= 2 here
-		b = min(max(b, 5), LOCAL_BITS);
+		b = min(max(b + LOCAL_EXTRA_BITS, 5), LOCAL_BITS);
 		b = min(b, top + 1);
 		const int shift = top + 1 - b;
 		const uint32_t nb = 1u << b, dmask = nb - 1;
-		// thread t owns the 8 consecutive digits 8t .. 8t+7 and keeps them as two 16-byte
-		// chunks at chunk indices t and THREADS + t: the scan reads and writes them with
-		// conflict-free 16-byte accesses
-#define MSB64_BIN_SLOT(d) ((((d) & 4u) << 9) | (((d) >> 3) << 2) | ((d) & 3u))
-		static_assert(LOCAL_NBINS == 8 * THREADS, "two chunks of four bins per thread");
+		// thread t owns the PER (8 or 16) consecutive digits t*PER .. t*PER+PER-1 and keeps
+		// them as 16-byte chunks of four at chunk indices c*OWNERS + t: the scan reads and
+		// writes them with conflict-free 16-byte accesses
+		constexpr int LPER = LOCAL_LPER, CH = LOCAL_CHUNKS;
+#define MSB64_BIN_SLOT(d) ((((((d) >> 2) & (CH - 1)) * OWNERS + ((d) >> LPER)) << 2) | ((d) & 3u))
 		// do the digit bits cover every differing bit?  then equal digit = equal key
 		const bool resolved = (diff & ((1ull << shift) - 1)) == 0;
 
@@ -183,16 +217,20 @@ local_sort_kernel(const Ctx c)
 		uint32_t nlist;
 		{
 			uint4 *b4 = reinterpret_cast<uint4 *>(bins);
-			const bool own = (tid << 3) < nb;
-			uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-			if (own) {
-				v0 = b4[tid];
-				v1 = b4[THREADS + tid];
+			const bool own = tid < OWNERS && (tid << LPER) < nb;
+			uint32_t cn[4 * CH];
+#pragma unroll
+			for (int ch = 0; ch < CH; ++ch) {
+				uint4 v = make_uint4(0u, 0u, 0u, 0u);
+				if (own) v = b4[ch * OWNERS + tid];
+				cn[4 * ch] = v.x;
+				cn[4 * ch + 1] = v.y;
+				cn[4 * ch + 2] = v.z;
+				cn[4 * ch + 3] = v.w;
 			}
-			const uint32_t cn[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 			uint32_t sum = 0;
 #pragma unroll
-			for (int q = 0; q < 8; ++q) {
+			for (int q = 0; q < 4 * CH; ++q) {
 				sum += cn[q];
 				if (!resolved && cn[q] - 2u <= LOCAL_SERIAL_MAX - 2u) sum += 1u << 16;
 			}
@@ -201,18 +239,19 @@ local_sort_kernel(const Ctx c)
 			nlist = total >> 16;
 			if (own) {
 				uint32_t base = ex & 0xffffu, at = ex >> 16;
-				uint32_t o[8];
 #pragma unroll
-				for (int q = 0; q < 8; ++q) {
-					o[q] = base | (cn[q] << 16);
+				for (int q = 0; q < 4 * CH; ++q) {
+					const uint32_t o = base | (cn[q] << 16);
 					base += cn[q];
 					if (!resolved && cn[q] >= 2u) {
-						if (cn[q] <= LOCAL_SERIAL_MAX) list[at++] = o[q];
-						else big[atomicAdd(&s_nbig, 1u)] = o[q];
+						if (cn[q] <= LOCAL_SERIAL_MAX) list[at++] = o;
+						else big[atomicAdd(&s_nbig, 1u)] = o;
 					}
+					cn[q] = o;
 				}
-				b4[tid] = make_uint4(o[0], o[1], o[2], o[3]);
-				b4[THREADS + tid] = make_uint4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+				for (int ch = 0; ch < CH; ++ch)
+					b4[ch * OWNERS + tid] = make_uint4(cn[4 * ch], cn[4 * ch + 1], cn[4 * ch + 2], cn[4 * ch + 3]);
 			}
 		}
 		__syncthreads();
@@ -230,12 +269,56 @@ local_sort_kernel(const Ctx c)
 				}
 			}
 		__syncthreads();
-		// 3b. one thread per short colliding bin: insertion sort in place
+		// the registers are free: request the next unit's pairs now
+		if (more) {
+			next = c.units[u + gridDim.x];
+			load_unit(next);
+		}
+		// 3b. one thread per short colliding bin.  Up to four pairs (nearly all of them):
+		//     loaded at once, ordered in registers by a 5-comparator network, stored back --
+		//     one shared-memory round trip instead of a chain of dependent ones.  Missing
+		//     slots hold the largest key and are never moved down (exchanges are strict).
 		const uint32_t nbig = s_nbig;     // read before the next barrier: thread 0 resets it for the next unit after it
 		for (uint32_t q = tid; q < nlist; q += THREADS) {
 			const uint32_t pk = list[q];
 			uint64_t *bk = skeys + (pk & 0xffffu), *br = srids + (pk & 0xffffu);
 			const uint32_t cnt = pk >> 16;
+			if (cnt <= 4) {
+				uint64_t a0 = bk[0], a1 = bk[1], b0 = br[0], b1 = br[1];
+				uint64_t a2 = ~0ull, a3 = ~0ull, b2 = 0, b3 = 0;
+				if (cnt > 2) {
+					a2 = bk[2];
+					b2 = br[2];
+				}
+				if (cnt > 3) {
+					a3 = bk[3];
+					b3 = br[3];
+				}
+#define MSB64_CE(x, y, rx, ry)                                                   \
+	{                                                                         \
+		const bool sw = x > y;                                            \
+		const uint64_t tx = sw ? y : x, ty = sw ? x : y;                  \
+		const uint64_t trx = sw ? ry : rx, try_ = sw ? rx : ry;           \
+		x = tx; y = ty; rx = trx; ry = try_;                              \
+	}
+				MSB64_CE(a0, a1, b0, b1)
+				MSB64_CE(a2, a3, b2, b3)
+				MSB64_CE(a0, a2, b0, b2)
+				MSB64_CE(a1, a3, b1, b3)
+				MSB64_CE(a1, a2, b1, b2)
+#undef MSB64_CE
+				bk[0] = a0; br[0] = b0;
+				bk[1] = a1; br[1] = b1;
+				if (cnt > 2) {
+					bk[2] = a2;
+					br[2] = b2;
+				}
+				if (cnt > 3) {
+					bk[3] = a3;
+					br[3] = b3;
+				}
+				continue;
+			}
 			for (uint32_t i = 1; i < cnt; ++i) {
 				const uint64_t key = bk[i];
 				uint32_t at = i;
