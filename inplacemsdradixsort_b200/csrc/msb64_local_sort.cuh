@@ -245,7 +245,7 @@ local_sort_kernel(const Ctx c)
 					base += cn[q];
 					if (!resolved && cn[q] >= 2u) {
 						if (cn[q] <= LOCAL_SERIAL_MAX) list[at++] = o;
-						else big[atomicAdd(&s_nbig, 1u)] = o;
+						else big[atomicAdd(&s_nbig, 1u)] = uint32_t((((q >> 2) * OWNERS + tid) << 2) | (q & 3));   // where the bin sits in the table
 					}
 					cn[q] = o;
 				}
@@ -269,6 +269,26 @@ local_sort_kernel(const Ctx c)
 				}
 			}
 		__syncthreads();
+		const uint32_t nbig = s_nbig;     // read before the next barrier: thread 0 resets it for the next unit after it
+		if (nbig) {
+			// long bins (duplicate-heavy or adversarial keys): a bin whose keys are all equal
+			// needs no ordering.  Every key of a long bin compares itself with the bin's first
+			// key and flags the bin (bit 31 of its table entry) when it differs.
+#pragma unroll
+			for (int j = 0; j < ITEMS; ++j)
+				if (j < rows) {
+					const uint32_t i = j * THREADS + tid;
+					if (i < size) {
+						const uint32_t d = uint32_t((k[j] - origin) >> shift) & dmask;
+						const uint32_t pk = bins[MSB64_BIN_SLOT(d)];
+						if (((pk >> 16) & 0x7fffu) > LOCAL_SERIAL_MAX && !(pk >> 31) &&
+						    skeys[pk & 0xffffu] != k[j])
+							atomicOr(&bins[MSB64_BIN_SLOT(d)], 1u << 31);
+					}
+				}
+			__syncthreads();
+			if (tid < nbig) big[tid] = bins[big[tid]];      // table position -> base | size << 16 | differs << 31
+		}
 		// the registers are free: request the next unit's pairs now
 		if (more) {
 			next = c.units[u + gridDim.x];
@@ -278,7 +298,6 @@ local_sort_kernel(const Ctx c)
 		//     loaded at once, ordered in registers by a 5-comparator network, stored back --
 		//     one shared-memory round trip instead of a chain of dependent ones.  Missing
 		//     slots hold the largest key and are never moved down (exchanges are strict).
-		const uint32_t nbig = s_nbig;     // read before the next barrier: thread 0 resets it for the next unit after it
 		for (uint32_t q = tid; q < nlist; q += THREADS) {
 			const uint32_t pk = list[q];
 			uint64_t *bk = skeys + (pk & 0xffffu), *br = srids + (pk & 0xffffu);
@@ -337,9 +356,10 @@ local_sort_kernel(const Ctx c)
 			}
 		}
 		__syncthreads();
+		// 3c. long bins whose keys are not all equal (adversarial bit patterns): block-wide network
 		for (uint32_t q = 0; q < nbig; ++q) {
 			const uint32_t pk = big[q];
-			block_bitonic(skeys + (pk & 0xffffu), srids + (pk & 0xffffu), pk >> 16);
+			if (pk >> 31) block_bitonic(skeys + (pk & 0xffffu), srids + (pk & 0xffffu), (pk >> 16) & 0x7fffu);
 		}
 
 		// 4. home (the next unit's first barrier orders these reads before its stores)

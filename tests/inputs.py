@@ -21,6 +21,15 @@ def make(kind: str, n: int, seed: int = 1) -> np.ndarray:
     if kind == "dup1000":
         vals = rng.integers(0, 1 << 64, size=1000, dtype=np.uint64)
         return vals[rng.integers(0, 1000, size=n)]
+    if kind == "dupmid":           # ~700 copies of each value: long all-equal bins inside local-sort units
+        vals = rng.integers(0, 1 << 64, size=max(n // 700, 1), dtype=np.uint64)
+        return vals[rng.integers(0, vals.size, size=n)]
+    if kind == "duppair":          # long bins holding two different keys each (not all equal)
+        vals = rng.integers(0, 1 << 64, size=max(n // 1400, 1), dtype=np.uint64) & ~np.uint64(1)
+        return vals[rng.integers(0, vals.size, size=n)] | rng.integers(0, 2, size=n).astype(np.uint64)
+    if kind == "dup36":            # ~36 copies of each value: long bins, some holding two values
+        vals = rng.integers(0, 1 << 64, size=max(n // 36, 1), dtype=np.uint64)
+        return vals[rng.integers(0, vals.size, size=n)]
     if kind == "equal":
         return np.full(n, 0xDEADBEEFCAFEF00D, dtype=np.uint64)
     if kind == "zero":
@@ -60,6 +69,6 @@ def make(kind: str, n: int, seed: int = 1) -> np.ndarray:
     raise ValueError(kind)
 
 
-KINDS = ["uniform", "low24", "low8", "high8", "dup16", "dup1000", "equal", "zero", "ones",
+KINDS = ["uniform", "low24", "low8", "high8", "dup16", "dup1000", "dupmid", "duppair", "dup36", "equal", "zero", "ones",
          "sorted", "reverse", "iota", "iota_rev", "skew", "zipf", "pow2", "outlier", "midbits",
          "two", "clustered"]
