@@ -98,6 +98,16 @@ int msb64_b200_sort_device(uint64_t *d_keys, uint64_t *d_rids, uint64_t n,
 			   void *workspace, size_t workspace_bytes,
 			   void *stream, uint64_t *phase_us);
 
+/* The same sort when every key is known to lie in [key_lo, key_hi] (a range partition's
+ * share, msb_64.c:1546-1606: after the reference's range partition a thread's keys lie
+ * between two delimiters).  The digit schedule is made for the bits that vary inside the
+ * range and the first digit is taken relative to key_lo, so a narrow range costs fewer
+ * passes.  A key outside the range makes the result undefined (it is not checked). */
+int msb64_b200_sort_device_range(uint64_t *d_keys, uint64_t *d_rids, uint64_t n,
+				 void *workspace, size_t workspace_bytes,
+				 void *stream, uint64_t *phase_us,
+				 uint64_t key_lo, uint64_t key_hi);
+
 /* Phases reported by msb64_b200_sort_device (indices into phase_us). */
 #define MSB64_PHASE_HISTOGRAM 0	/* per-digit histogram kernels        (msb_64.c:701-738)  */
 #define MSB64_PHASE_PLAN      1	/* bucket scans / work lists          (msb_64.c:1020-1034) */

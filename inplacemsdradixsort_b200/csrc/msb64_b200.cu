@@ -68,10 +68,11 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------ schedule
 std::vector<int> g_schedule_override;
 
-// Digit widths, most significant first (the role of schedule_passes, msb_64.c:1334).
-std::vector<int> make_schedule(uint64_t n)
+// Digit widths, most significant first (the role of schedule_passes, msb_64.c:1334), for
+// keys of which only the low `width` bits vary (64 when nothing is known about the keys).
+std::vector<int> make_schedule(uint64_t n, int width = 64)
 {
-	if (!g_schedule_override.empty()) return g_schedule_override;
+	if (width == 64 && !g_schedule_override.empty()) return g_schedule_override;
 	// Uniform keys stop descending once the average bucket fits the local sort with
 	// room to spare (2048 pairs): that takes `need` bits.  The scatter's HBM efficiency
 	// falls with the run length TILE / 2^bits (tools/permcopy.cu: 6.3 TB/s at 256-byte
@@ -79,7 +80,8 @@ std::vector<int> make_schedule(uint64_t n)
 	// passes of at most 8 bits, as evenly as possible, widest first.
 	int log_n = 0;
 	while (log_n < 63 && (1ull << log_n) < n) ++log_n;
-	const int need = log_n > 11 ? log_n - 11 : 0;
+	int need = log_n > 11 ? log_n - 11 : 0;
+	if (need > width) need = width;
 	std::vector<int> s;
 	int used = 0;
 	if (need >= 4) {
@@ -91,18 +93,44 @@ std::vector<int> make_schedule(uint64_t n)
 			used += b;
 		}
 	}
-	// the rest of the key (only skewed inputs get here): 8-bit digits, widths 4..11 at the end
-	int rest = 64 - used;
-	while (rest >= 16 || rest == 8) {
-		s.push_back(8);
-		rest -= 8;
+	// the rest of the key (only skewed inputs get here): 8-bit digits, 4..8 bits at the end.
+	// The last digit may reach above `width` (those bits are equal in every key).
+	int rest = width - used;
+	while (rest > 0) {
+		int b = rest <= 8 ? (rest < 4 ? 4 : rest) : (rest < 12 ? rest - rest / 2 : 8);
+		s.push_back(b);
+		rest -= b;
 	}
-	if (rest > 11) {
-		s.push_back(rest - rest / 2);
-		rest /= 2;
-	}
-	if (rest) s.push_back(rest);
+	if (s.empty()) s.push_back(4);
 	return s;
+}
+
+// Level-0 digit of a sort whose keys are known to lie in [lo, hi]: (key >> shift0) - origin0
+// with the schedule made for the bits that actually vary.  Returns the schedule; the
+// digits below level 0 are plain bit fields under shift0.
+struct RangePlan {
+	std::vector<int> sched;
+	int shift0;
+	uint64_t origin0;       // lo >> shift0
+};
+
+RangePlan plan_range(uint64_t n, uint64_t lo, uint64_t hi)
+{
+	RangePlan r;
+	if (hi < lo) hi = lo;
+	const uint64_t span = hi - lo;
+	int width = 0;
+	while (width < 64 && (span >> width)) ++width;
+	if (width < 1) width = 1;
+	for (;; ++width) {
+		r.sched = make_schedule(n, width);
+		const int bits0 = r.sched[0];
+		r.shift0 = width > bits0 ? width - bits0 : 0;
+		r.origin0 = lo >> r.shift0;
+		// the digit of the largest key must fit: (hi >> shift0) - origin0 < 2^bits0
+		if (width >= 64 || ((hi >> r.shift0) - r.origin0) < (1ull << bits0)) break;
+	}
+	return r;
 }
 
 // ------------------------------------------------------------------ device state
@@ -215,23 +243,24 @@ Layout make_layout(uint64_t n, const std::vector<int> &sched)
 
 // ------------------------------------------------------------------ launches
 template <int BITS>
-void launch_level(const Ctx &c, int level, int shift, int next_bits, cudaStream_t st,
+void launch_level(const Ctx &c, int level, int shift, uint32_t origin, int next_bits, cudaStream_t st,
 		  cudaEvent_t *ev)
 {
 	using H = HistCfg<BITS, 256>;
 	using S = ScatterCfg<BITS, SCATTER_THREADS>;
 	if (ev) cudaEventRecord(ev[0], st);
-	histogram_kernel<BITS, 256><<<g_dev.sms * g_dev.hist_blocks[BITS], 256, H::SMEM, st>>>(c, level, shift);
+	histogram_kernel<BITS, 256><<<g_dev.sms * g_dev.hist_blocks[BITS], 256, H::SMEM, st>>>(c, level, shift, origin);
 	if (ev) cudaEventRecord(ev[1], st);
 	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits, shift);
 	if (ev) cudaEventRecord(ev[2], st);
-	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<g_dev.sms * g_dev.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, shift);
+	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<g_dev.sms * g_dev.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, shift, origin);
 	if (ev) cudaEventRecord(ev[3], st);
 	g_launches += 3;
 }
 
 int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *workspace,
-		       size_t workspace_bytes, cudaStream_t st, uint64_t *phase_us)
+		       size_t workspace_bytes, cudaStream_t st, uint64_t *phase_us,
+		       uint64_t key_lo = 0, uint64_t key_hi = ~0ull)
 {
 	int rc = device_init();
 	if (rc) return rc;
@@ -241,7 +270,8 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	if (!d_keys || !d_rids || (uintptr_t(d_keys) & 15) || (uintptr_t(d_rids) & 15))
 		return fail(MSB64_ERR_ARG, "device arrays must be non-NULL and 16-byte aligned%s");
 
-	const std::vector<int> sched = make_schedule(n);
+	const RangePlan rp = plan_range(n, key_lo, key_hi);
+	const std::vector<int> &sched = rp.sched;
 	const Layout L = make_layout(n, sched);
 	if (!workspace) {
 		if (g_dev.ws_bytes < L.total) {
@@ -285,28 +315,30 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	init_kernel<<<g_dev.sms, 256, 0, st>>>(c, sched[0]);
 	g_launches += 1;
 	if (n > LOCAL_CAP) {
-		int shift = 64;
+		int shift = rp.shift0 + sched[0];
 		for (int l = 0; l < levels; ++l) {
 			const int bits = sched[l];
-			shift -= bits;
+			shift = shift > bits ? shift - bits : 0;
+			const uint32_t origin = l == 0 ? uint32_t(rp.origin0) : 0u;
 			const int next_bits = l + 1 < levels ? sched[l + 1] : 0;
 			cudaEvent_t *lev = ev ? ev + 1 + 4 * l : nullptr;
 			switch (bits) {
-			case 4: launch_level<4>(c, l, shift, next_bits, st, lev); break;
-			case 5: launch_level<5>(c, l, shift, next_bits, st, lev); break;
-			case 6: launch_level<6>(c, l, shift, next_bits, st, lev); break;
-			case 7: launch_level<7>(c, l, shift, next_bits, st, lev); break;
-			case 8: launch_level<8>(c, l, shift, next_bits, st, lev); break;
-			case 9: launch_level<9>(c, l, shift, next_bits, st, lev); break;
-			case 10: launch_level<10>(c, l, shift, next_bits, st, lev); break;
-			case 11: launch_level<11>(c, l, shift, next_bits, st, lev); break;
+			case 4: launch_level<4>(c, l, shift, origin, next_bits, st, lev); break;
+			case 5: launch_level<5>(c, l, shift, origin, next_bits, st, lev); break;
+			case 6: launch_level<6>(c, l, shift, origin, next_bits, st, lev); break;
+			case 7: launch_level<7>(c, l, shift, origin, next_bits, st, lev); break;
+			case 8: launch_level<8>(c, l, shift, origin, next_bits, st, lev); break;
+			case 9: launch_level<9>(c, l, shift, origin, next_bits, st, lev); break;
+			case 10: launch_level<10>(c, l, shift, origin, next_bits, st, lev); break;
+			case 11: launch_level<11>(c, l, shift, origin, next_bits, st, lev); break;
 			default: return fail(MSB64_ERR_ARG, "digit width outside 4..11%s");
 			}
 		}
 	}
 	cudaEvent_t *tail = ev ? ev + 1 + 4 * levels : nullptr;
 	if (tail) cudaEventRecord(tail[0], st);
-	local_sort_kernel<<<g_dev.sms * g_dev.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(c);
+	local_sort_kernel<<<g_dev.sms * g_dev.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(
+		c, uint32_t(rp.shift0), rp.origin0 << rp.shift0);
 	if (tail) cudaEventRecord(tail[1], st);
 	copy_kernel<<<g_dev.sms * 8, 256, 0, st>>>(c);
 	if (tail) cudaEventRecord(tail[2], st);
@@ -568,6 +600,16 @@ int msb64_b200_sort_device(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void 
 	std::lock_guard<std::mutex> lock(g_mutex);
 	return sort_device_locked(d_keys, d_rids, n, workspace, workspace_bytes,
 				  static_cast<cudaStream_t>(stream), phase_us);
+}
+
+int msb64_b200_sort_device_range(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *workspace,
+				 size_t workspace_bytes, void *stream, uint64_t *phase_us,
+				 uint64_t key_lo, uint64_t key_hi)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	if (key_hi < key_lo) return fail(MSB64_ERR_ARG, "key_hi < key_lo%s");
+	return sort_device_locked(d_keys, d_rids, n, workspace, workspace_bytes,
+				  static_cast<cudaStream_t>(stream), phase_us, key_lo, key_hi);
 }
 
 int msb64_b200_get_schedule(uint64_t n, int *bits)

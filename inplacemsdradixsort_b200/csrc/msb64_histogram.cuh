@@ -8,6 +8,9 @@
 // A warp whose 32 keys all carry the same digit (presorted or low-entropy inputs)
 // adds once instead of serialising 32 atomics on one address.  The block histogram is
 // added to the segment's global counters whenever the block moves to another segment.
+// `origin`: digit of the smallest possible key at this level (level 0 of a sort whose key
+// range is known, see make_schedule in msb64_b200.cu; 0 everywhere else): the digit is
+// (key >> shift) - origin.
 #pragma once
 #include "msb64_common.cuh"
 
@@ -26,13 +29,13 @@ struct HistCfg {
 // or low-entropy input) adds once instead of serialising on one address.
 template <int ITEMS, int NB>
 __device__ __forceinline__ void hist_add_tile(uint32_t *h, const uint64_t (&k)[ITEMS], int shift,
-					      uint32_t validmask)
+					      uint32_t origin, uint32_t validmask)
 {
 	// keys outside the segment count into a per-lane dummy bin behind the real ones
 	uint32_t d[ITEMS];
 #pragma unroll
 	for (int j = 0; j < ITEMS; ++j)
-		d[j] = ((validmask >> j) & 1u) ? (uint32_t(k[j] >> shift) & (NB - 1)) : NB + lane_id();
+		d[j] = ((validmask >> j) & 1u) ? ((uint32_t(k[j] >> shift) - origin) & (NB - 1)) : NB + lane_id();
 	const uint32_t d0 = __shfl_sync(0xffffffffu, d[0], 0);
 	bool same = true;
 #pragma unroll
@@ -47,7 +50,7 @@ __device__ __forceinline__ void hist_add_tile(uint32_t *h, const uint64_t (&k)[I
 
 template <int BITS, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-histogram_kernel(const Ctx c, const int level, const int shift)
+histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t origin)
 {
 	using Cfg = HistCfg<BITS, THREADS>;
 	constexpr int NB = Cfg::NB, ITEMS = Cfg::ITEMS;
@@ -106,7 +109,7 @@ histogram_kernel(const Ctx c, const int level, const int shift)
 				validmask |= uint32_t(valid) << j;
 			}
 		}
-		hist_add_tile<ITEMS, NB>(sh, k, shift, validmask);
+		hist_add_tile<ITEMS, NB>(sh, k, shift, origin, validmask);
 	}
 	if (cur_seg != 0xffffffffu) {
 		__syncthreads();

@@ -117,7 +117,7 @@ __device__ __forceinline__ void tile_ranks(uint32_t *cnt, uint32_t (&d)[ITEMS])
 
 template <int BITS, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-scatter_kernel(const Ctx c, const int level, const int shift)
+scatter_kernel(const Ctx c, const int level, const int shift, const uint32_t origin)
 {
 	using Cfg = ScatterCfg<BITS, THREADS>;
 	constexpr int NB = Cfg::NB, ITEMS = Cfg::ITEMS, BPT = Cfg::BPT;
@@ -221,8 +221,8 @@ scatter_kernel(const Ctx c, const int level, const int shift)
 #pragma unroll
 			for (int jj = 0; jj < ITEMS / 2; ++jj) {
 				const ulonglong2 v = k2[jj * THREADS + tid];
-				dr[2 * jj] = uint32_t(v.x >> shift) & (NB - 1);
-				dr[2 * jj + 1] = uint32_t(v.y >> shift) & (NB - 1);
+				dr[2 * jj] = (uint32_t(v.x >> shift) - origin) & (NB - 1);
+				dr[2 * jj + 1] = (uint32_t(v.y >> shift) - origin) & (NB - 1);
 			}
 			if (!full) {
 #pragma unroll
@@ -271,7 +271,7 @@ scatter_kernel(const Ctx c, const int level, const int shift)
 			const uint32_t s = sidx[i];
 			const uint64_t key = kin[s];
 			const uint64_t rid = rin[s];
-			const uint32_t dst = delta[uint32_t(key >> shift) & (NB - 1)] + i;
+			const uint32_t dst = delta[(uint32_t(key >> shift) - origin) & (NB - 1)] + i;
 			st_stream_u64(dst_keys + dst, key);
 			st_stream_u64(dst_rids + dst, rid);
 		}

@@ -97,9 +97,9 @@ class CudaOps:
                                             table.data_ptr(), world, cursors.data_ptr(),
                                             out_keys.data_ptr(), out_rids.data_ptr(), self._stream()))
 
-    def sort(self, keys, rids, n, ws, ws_bytes):
-        _m._raise(self.lib.msb64_b200_sort_device(keys.data_ptr(), rids.data_ptr(), n, ws.data_ptr(),
-                                                  ws_bytes, self._stream(), None))
+    def sort(self, keys, rids, n, ws, ws_bytes, key_lo=0, key_hi=(1 << 64) - 1):
+        _m._raise(self.lib.msb64_b200_sort_device_range(keys.data_ptr(), rids.data_ptr(), n, ws.data_ptr(),
+                                                        ws_bytes, self._stream(), None, key_lo, key_hi))
 
 
 # --------------------------------------------------------------------- the sorter
@@ -195,7 +195,15 @@ class ShardedSorter:
             ins, outs = [int(x) for x in send], [int(x) for x in recv]
             dist.all_to_all_single(self.recv_keys[:total], self.send_keys[:n], outs, ins, group=self.group)
             dist.all_to_all_single(self.recv_rids[:total], self.send_rids[:n], outs, ins, group=self.group)
-        self.ops.sort(self.recv_keys, self.recv_rids, total, self.ws, self.ws_bytes)
+        # this rank's keys lie in its bin range: the local sort spends no pass on the bits
+        # the range partition already fixed
+        mine = np.nonzero(table == self.rank)[0]
+        if mine.size:
+            key_lo = int(mine[0]) << self.shift
+            key_hi = ((int(mine[-1]) + 1) << self.shift) - 1
+        else:
+            key_lo, key_hi = 0, (1 << 64) - 1
+        self.ops.sort(self.recv_keys, self.recv_rids, total, self.ws, self.ws_bytes, key_lo, key_hi)
         return self.recv_keys[:total], self.recv_rids[:total], total
 
     # -- acceptance across ranks (the cross-node half of check(), msb_64.c:2485-2495)

@@ -31,7 +31,8 @@ ERRORS = {-1: "CUDA", -2: "ARG", -3: "TOO_BIG", -4: "CAPACITY", -5: "NOMEM", -6:
 # every symbol include/msb64_b200.h declares (checked by tests without a GPU)
 EXPORTS = (
     "sort", "mamalloc", "msb64_b200_sort", "msb64_b200_sort_host",
-    "msb64_b200_workspace_bytes", "msb64_b200_sort_device", "msb64_b200_get_schedule",
+    "msb64_b200_workspace_bytes", "msb64_b200_sort_device", "msb64_b200_sort_device_range",
+    "msb64_b200_get_schedule",
     "msb64_b200_set_schedule", "msb64_b200_device_count", "msb64_b200_last_error",
     "msb64_b200_launch_count", "msb64_b200_last_stats", "msb64_b200_last_level_times",
     "msb64_b200_host_alloc",
@@ -81,6 +82,9 @@ def load_library() -> C.CDLL:
     L.msb64_b200_sort_device.restype = C.c_int
     L.msb64_b200_sort_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                          C.c_size_t, C.c_void_p, _u64p]
+    L.msb64_b200_sort_device_range.restype = C.c_int
+    L.msb64_b200_sort_device_range.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                               C.c_size_t, C.c_void_p, _u64p, C.c_uint64, C.c_uint64]
     L.msb64_b200_get_schedule.restype = C.c_int
     L.msb64_b200_get_schedule.argtypes = [C.c_uint64, C.POINTER(C.c_int)]
     L.msb64_b200_set_schedule.restype = C.c_int
@@ -303,14 +307,20 @@ def workspace_bytes(n: int) -> int:
 
 
 def sort_device(keys_ptr: int, rids_ptr: int, n: int, workspace_ptr: int | None = None,
-                workspace_bytes_: int = 0, stream: int | None = None, timed: bool = False):
+                workspace_bytes_: int = 0, stream: int | None = None, timed: bool = False,
+                key_range: tuple[int, int] | None = None):
     """Sort n device-resident pairs in place.  Pointers are plain integers (a torch
     tensor's data_ptr(), a DeviceArray's ptr, ...).  Enqueues on `stream` without
-    synchronising unless timed=True, which returns {phase: microseconds}."""
+    synchronising unless timed=True, which returns {phase: microseconds}.
+    key_range=(lo, hi): every key is known to lie in [lo, hi] (msb64_b200_sort_device_range)."""
     L = load_library()
     phase = (C.c_uint64 * len(PHASES))() if timed else None
-    _raise(L.msb64_b200_sort_device(keys_ptr, rids_ptr, n, workspace_ptr, workspace_bytes_,
-                                    stream, phase))
+    if key_range is None:
+        _raise(L.msb64_b200_sort_device(keys_ptr, rids_ptr, n, workspace_ptr, workspace_bytes_,
+                                        stream, phase))
+    else:   # every key lies in [lo, hi]: fewer passes for a narrow range
+        _raise(L.msb64_b200_sort_device_range(keys_ptr, rids_ptr, n, workspace_ptr, workspace_bytes_,
+                                              stream, phase, int(key_range[0]), int(key_range[1])))
     return dict(zip(PHASES, (int(x) for x in phase))) if timed else None
 
 

@@ -59,9 +59,11 @@ class NumpyOps:
         out_keys[:n] = keys[:n][torch.from_numpy(order)]
         out_rids[:n] = rids[:n][torch.from_numpy(order)]
 
-    def sort(self, keys, rids, n, ws, ws_bytes):
+    def sort(self, keys, rids, n, ws, ws_bytes, key_lo=0, key_hi=(1 << 64) - 1):
         if n == 0:
             return
+        kk = keys[:n].numpy().view(np.uint64)
+        assert int(kk.min()) >= key_lo and int(kk.max()) <= key_hi, "received keys outside the rank's range"
         k = np.concatenate([keys[:n].numpy().view(np.uint64), np.zeros(n // 2 + 64, np.uint64)])
         r = np.concatenate([rids[:n].numpy().view(np.uint64), np.zeros(n // 2 + 64, np.uint64)])
         self.oracle.sort([k], [r], [n])

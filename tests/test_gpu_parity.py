@@ -141,3 +141,31 @@ def test_device_resident_and_digest(gpu, oracle):
         assert np.array_equal(out, np.sort(keys))
         stats = gpu.last_stats()
         assert stats["error"] == 0
+
+
+RANGES = [
+    (0, (1 << 64) - 1), (5, 5), (7, 8), (0x1234_5678_0000_0000, 0x1234_5678_0000_0FFF),
+    (0x7FFF_FFFF_FFFF_FF00, 0x8000_0000_0000_00FF), ((1 << 61), (1 << 62) - 1),
+    (3 << 61, (4 << 61) - 1), (0xABC << 52, (0xDEF << 52) + 12345), (1, 1 << 33),
+    ((1 << 64) - 1000, (1 << 64) - 1), (0x00FF_0000_0000_0001, 0x0100_0000_0000_0000),
+]
+
+
+@pytest.mark.parametrize("lo,hi", RANGES)
+@pytest.mark.parametrize("n", [2, 4097, 300_001, 1 << 21])
+def test_sort_with_known_key_range(gpu, lo, hi, n):
+    """msb64_b200_sort_device_range: origin-relative first digit, schedule made for the span."""
+    rng = np.random.default_rng(n ^ (lo & 0xFFFF))
+    span = hi - lo
+    off = rng.integers(0, 1 << 64, size=n, dtype=np.uint64)
+    keys = (np.uint64(lo) + (off % np.uint64(span + 1) if span < (1 << 64) - 1 else off)).astype(np.uint64)
+    keys[0], keys[-1] = np.uint64(lo), np.uint64(hi)               # both ends of the range occur
+    rids = np.arange(n, dtype=np.uint64) + np.uint64(77)
+    with gpu.DeviceArray(n) as dk, gpu.DeviceArray(n) as dr:
+        dk.upload(keys)
+        dr.upload(rids)
+        gpu.sort_device(dk.ptr, dr.ptr, n, key_range=(lo, hi))
+        gk, gr = dk.download(), dr.download()
+    order = np.lexsort((rids, keys))
+    assert np.array_equal(gk, keys[order])
+    assert np.array_equal(gr[np.lexsort((gr, gk))], rids[order])
