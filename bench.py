@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--pairs-per-gpu", type=str, default="1<<30")
     ap.add_argument("--cpu-sample", type=str, default="1<<27",
                     help="pairs per step of the CPU reference (it refuses < 2^25)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: fused peer-memory route+exchange kernel, or route + NCCL all-to-all")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -248,7 +250,7 @@ def main_b200(args):
     sorter = None
     if dist is not None:
         from inplacemsdradixsort_b200.distributed import ShardedSorter
-        sorter = ShardedSorter(n, dev)
+        sorter = ShardedSorter(n, dev, exchange=args.exchange)
 
     def one_step():
         if sorter is None:
@@ -324,7 +326,10 @@ def main_b200(args):
             "l2": "inputs (16 B x pairs per GPU) far exceed the 126 MB L2; every step re-reads "
                   "a fresh unsorted copy",
             "schedule_bits": m.get_schedule(n),
-            "parallelism": "single GPU" if world == 1 else f"range partition over {world} GPUs (NCCL all-to-all)",
+            "parallelism": "single GPU" if world == 1 else
+                           f"range partition over {world} GPUs, exchange = " +
+                           ("routing kernel storing into the peers' HBM over NVLink (CUDA IPC)"
+                            if sorter.exchange == "peer" else "route kernel + NCCL all-to-all"),
         },
         "clocks": clocks, "gpu_launches": launches, "verified": True,
     }

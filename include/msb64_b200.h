@@ -189,6 +189,28 @@ int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
 		     uint32_t *d_cursors, uint64_t *d_out_keys, uint64_t *d_out_rids,
 		     void *stream);
 
+/* Fused route + exchange over peer memory: the same kernel, but destination d has its own
+ * output arrays out_keys[d] / out_rids[d] (HOST arrays of ndest device pointers) -- the
+ * receive buffers of the destination GPUs, the local one for this rank and, for the
+ * others, mappings obtained with msb64_b200_ipc_open.  The kernel's stores go over
+ * NVLink / NVSwitch straight into the destination's HBM; there is no separate exchange
+ * pass (the NCCL all-to-all of the unfused path).  d_cursors[d] = first slot of THIS
+ * source inside destination d's arrays (the pairs lower-ranked sources send to d).  The
+ * caller orders the kernel against the peers' use of their buffers (a collective before
+ * and after; see distributed.py).
+ *
+ * msb64_b200_ipc_export / _open / _close: CUDA IPC handle (64 bytes) of an allocation made
+ * with msb64_b200_device_alloc, to be sent to the other processes of the box; _open maps
+ * a peer's allocation and enables peer access; returns NULL on failure. */
+#define MSB64_IPC_HANDLE_BYTES 64
+int msb64_b200_route_peer(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
+			  int shift, int bits, const uint8_t *d_bin_to_dest, int ndest,
+			  uint32_t *d_cursors, uint64_t *const *out_keys,
+			  uint64_t *const *out_rids, void *stream);
+int msb64_b200_ipc_export(void *d_ptr, void *handle64);
+void *msb64_b200_ipc_open(const void *handle64);
+int msb64_b200_ipc_close(void *mapped);
+
 #ifdef __cplusplus
 }
 #endif

@@ -696,11 +696,10 @@ int msb64_b200_digit_histogram(const uint64_t *d_keys, uint64_t n, int shift, in
 	return MSB64_OK;
 }
 
-int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, int shift, int bits,
-		     const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors,
-		     uint64_t *d_out_keys, uint64_t *d_out_rids, void *stream)
+static int route_common(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, int shift, int bits,
+			const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors, const RouteDst &dst,
+			void *stream)
 {
-	std::lock_guard<std::mutex> lock(g_mutex);
 	int rc = device_init();
 	if (rc) return rc;
 	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift + bits > 64 || ndest < 1 ||
@@ -715,9 +714,68 @@ int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
 		configured = true;
 	}
 	route_kernel<<<g_dev.sms * 2, ROUTE_THREADS, route_smem(bits), static_cast<cudaStream_t>(stream)>>>(
-		d_keys, d_rids, uint32_t(n), shift, bits, d_bin_to_dest, ndest, d_cursors, d_out_keys, d_out_rids);
+		d_keys, d_rids, uint32_t(n), shift, bits, d_bin_to_dest, ndest, d_cursors, dst);
 	g_launches += 1;
 	CUDA_TRY(cudaGetLastError());
+	return MSB64_OK;
+}
+
+int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, int shift, int bits,
+		     const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors,
+		     uint64_t *d_out_keys, uint64_t *d_out_rids, void *stream)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	RouteDst dst;
+	for (int i = 0; i < ROUTE_MAX_DEST; ++i) {
+		dst.keys[i] = d_out_keys;
+		dst.rids[i] = d_out_rids;
+	}
+	return route_common(d_keys, d_rids, n, shift, bits, d_bin_to_dest, ndest, d_cursors, dst, stream);
+}
+
+int msb64_b200_route_peer(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, int shift, int bits,
+			  const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors,
+			  uint64_t *const *out_keys, uint64_t *const *out_rids, void *stream)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	if (!out_keys || !out_rids || ndest < 1 || ndest > ROUTE_MAX_DEST)
+		return fail(MSB64_ERR_ARG, "route_peer: bad destination table%s");
+	RouteDst dst;
+	for (int i = 0; i < ROUTE_MAX_DEST; ++i) {
+		dst.keys[i] = out_keys[i < ndest ? i : 0];
+		dst.rids[i] = out_rids[i < ndest ? i : 0];
+	}
+	return route_common(d_keys, d_rids, n, shift, bits, d_bin_to_dest, ndest, d_cursors, dst, stream);
+}
+
+int msb64_b200_ipc_export(void *d_ptr, void *handle64)
+{
+	static_assert(sizeof(cudaIpcMemHandle_t) == MSB64_IPC_HANDLE_BYTES, "handle size");
+	if (!d_ptr || !handle64) return fail(MSB64_ERR_ARG, "ipc_export: NULL%s");
+	cudaIpcMemHandle_t h;
+	CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+	memcpy(handle64, &h, sizeof(h));
+	return MSB64_OK;
+}
+
+void *msb64_b200_ipc_open(const void *handle64)
+{
+	if (!handle64) return nullptr;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof(h));
+	void *p = nullptr;
+	cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+	if (e != cudaSuccess) {
+		snprintf(g_err, sizeof(g_err), "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+int msb64_b200_ipc_close(void *mapped)
+{
+	if (mapped) CUDA_TRY(cudaIpcCloseMemHandle(mapped));
 	return MSB64_OK;
 }
 

@@ -5,11 +5,17 @@
 //   digit_histogram_kernel  counts of the top `bits` key bits of a rank's slice; the
 //                           per-rank histograms are all-gathered and cut into one
 //                           contiguous bin range per rank by the host (distributed.py);
-//   route_kernel            groups the slice by destination rank (bin -> rank table), so
-//                           that every rank's share is one contiguous run to hand to
-//                           ncclSend.  With <= 64 destinations the runs written per tile
-//                           are long (>= 64 pairs), the regime in which the HBM write
-//                           path runs at copy speed (tools/permcopy.cu).
+//   route_kernel            groups the slice by destination rank (bin -> rank table).  Every
+//                           destination has its own output arrays: either slices of one
+//                           local send buffer (every rank's share is then one contiguous
+//                           run to hand to ncclSend), or -- the fused compute + exchange
+//                           form -- the receive buffers of the peer GPUs themselves, mapped
+//                           through CUDA IPC: the kernel's coalesced stores travel over
+//                           NVLink / NVSwitch straight into the destination's HBM and no
+//                           separate exchange pass exists.  With <= 64 destinations the
+//                           runs written per tile are long (>= 64 pairs, 512 bytes), the
+//                           regime in which both the HBM write path (tools/permcopy.cu)
+//                           and NVLink run at full rate.
 #pragma once
 #include "msb64_common.cuh"
 
@@ -39,12 +45,18 @@ digit_histogram_kernel(const uint64_t *keys, uint64_t n, int shift, int bits,
 		if (sh[i]) atomicAdd(&hist[i], (unsigned long long) sh[i]);
 }
 
-// cursors[d] = next free slot of destination d in the output (initialised by the host to
-// the exclusive prefix of the send counts).
+// Output arrays of every destination (kernel parameter, 1 KiB).
+struct RouteDst {
+	uint64_t *keys[ROUTE_MAX_DEST];
+	uint64_t *rids[ROUTE_MAX_DEST];
+};
+
+// cursors[d] = next free slot of this source in destination d's output arrays (initialised
+// by the host: exclusive prefix of the send counts for a local send buffer, number of pairs
+// the lower-ranked sources send to d for a peer's receive buffer).
 __global__ void __launch_bounds__(ROUTE_THREADS, 2)
 route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, int bits,
-	     const uint8_t *bin_to_dest, int ndest, uint32_t *cursors,
-	     uint64_t *out_keys, uint64_t *out_rids)
+	     const uint8_t *bin_to_dest, int ndest, uint32_t *cursors, const RouteDst dst)
 {
 	constexpr int THREADS = ROUTE_THREADS, ITEMS = ROUTE_ITEMS;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -53,11 +65,17 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 	uint32_t *cnt = reinterpret_cast<uint32_t *>(srids + TILE);           // [ROUTE_MAX_DEST + 32]
 	uint32_t *lbase = cnt + ROUTE_MAX_DEST + 32;                          // [ROUTE_MAX_DEST]
 	uint32_t *delta = lbase + ROUTE_MAX_DEST;                             // [ROUTE_MAX_DEST]
-	uint8_t *table = reinterpret_cast<uint8_t *>(delta + ROUTE_MAX_DEST); // [1 << bits]
+	uint64_t **okeys = reinterpret_cast<uint64_t **>(delta + ROUTE_MAX_DEST);   // [ROUTE_MAX_DEST]
+	uint64_t **orids = okeys + ROUTE_MAX_DEST;                             // [ROUTE_MAX_DEST]
+	uint8_t *table = reinterpret_cast<uint8_t *>(orids + ROUTE_MAX_DEST); // [1 << bits]
 
 	const uint32_t tid = threadIdx.x, lane = lane_id();
 	const uint32_t nb = 1u << bits;
 	for (uint32_t i = tid; i < nb; i += THREADS) table[i] = bin_to_dest[i];
+	if (tid < uint32_t(ndest)) {
+		okeys[tid] = dst.keys[tid];
+		orids[tid] = dst.rids[tid];
+	}
 	const uint32_t ntiles = (n + TILE - 1) / TILE;
 
 	for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -110,9 +128,10 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 		__syncthreads();
 		for (uint32_t i = tid; i < count; i += THREADS) {
 			const uint64_t key = skeys[i];
-			const uint32_t dst = delta[table[uint32_t(key >> shift) & (nb - 1)]] + i;
-			st_stream_u64(out_keys + dst, key);
-			st_stream_u64(out_rids + dst, srids[i]);
+			const uint32_t d = table[uint32_t(key >> shift) & (nb - 1)];
+			const uint32_t at = delta[d] + i;
+			st_stream_u64(okeys[d] + at, key);
+			st_stream_u64(orids[d] + at, srids[i]);
 		}
 		__syncthreads();
 	}
@@ -120,7 +139,8 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 
 constexpr size_t route_smem(int bits)
 {
-	return size_t(TILE) * 16 + (ROUTE_MAX_DEST + 32 + 2 * ROUTE_MAX_DEST) * 4 + (size_t(1) << bits);
+	return size_t(TILE) * 16 + (ROUTE_MAX_DEST + 32 + 2 * ROUTE_MAX_DEST) * 4 + 2 * ROUTE_MAX_DEST * 8
+	       + (size_t(1) << bits);
 }
 
 } // namespace msb64

@@ -11,9 +11,17 @@ partition into per-node ranges -> every thread sorts its range; msb_64.c:1546-16
        further agreement step is needed; the same table gives every send and
        receive count, no count exchange                              (host, tiny)
     4. the local pairs are grouped by destination rank               (device kernel)
-    5. keys and rids are exchanged                                    (NCCL all-to-all,
-       i.e. grouped ncclSend/ncclRecv over NVLink)
-    6. every rank sorts what it received with the single-GPU sort     (device kernels)
+    5. keys and rids are exchanged.  Two forms:
+       "peer"  steps 4 and 5 are ONE kernel: every rank maps the receive buffers of all
+               peers through CUDA IPC and the routing kernel's coalesced stores go over
+               NVLink / NVSwitch straight into the destination's HBM, at the offset the
+               all-gathered histograms assign to (source, destination); a one-word
+               all-reduce afterwards tells every rank that its buffer is complete
+       "nccl"  the routed pairs go to a local send buffer and through an NCCL
+               all-to-all (grouped ncclSend/ncclRecv) -- the unfused baseline, also what
+               the gloo tests exercise
+    6. every rank sorts what it received with the single-GPU sort, told the key range of
+       its share (msb64_b200_sort_device_range)                       (device kernels)
 
 Afterwards rank r holds the r-th key range in ascending order and every key of rank r
 is <= every key of rank r+1 (the contract of the reference's sort() across NUMA
@@ -64,8 +72,17 @@ def exchange_counts(hists: np.ndarray, table: np.ndarray, world: int) -> np.ndar
 
 
 # --------------------------------------------------------------------- device steps
+class _RawCuda:
+    """__cuda_array_interface__ view of `count` int64 slots at a raw device pointer."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<i8",
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
 class CudaOps:
     """The device steps on torch CUDA tensors through libmsb64_b200.so."""
+    supports_peer = True
 
     def __init__(self, device):
         import torch
@@ -97,6 +114,37 @@ class CudaOps:
                                             table.data_ptr(), world, cursors.data_ptr(),
                                             out_keys.data_ptr(), out_rids.data_ptr(), self._stream()))
 
+    # -- peer-memory exchange
+    def alloc_exportable(self, count):
+        """cudaMalloc'ed (IPC-exportable) int64 array: (raw pointer, torch view)."""
+        with self.torch.cuda.device(self.device):
+            ptr = self.lib.msb64_b200_device_alloc(max(int(count), 1) * 8)
+        if not ptr:
+            raise _m.Msb64Error(-5, f"device_alloc({count * 8} bytes)")
+        return ptr, self.torch.as_tensor(_RawCuda(ptr, count), device=self.device)
+
+    def free_exportable(self, ptr):
+        self.lib.msb64_b200_device_free(ptr)
+
+    def ipc_export(self, ptr) -> bytes:
+        buf = C.create_string_buffer(64)
+        _m._raise(self.lib.msb64_b200_ipc_export(ptr, buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes):
+        with self.torch.cuda.device(self.device):
+            return self.lib.msb64_b200_ipc_open(C.create_string_buffer(handle, 64))
+
+    def ipc_close(self, ptr):
+        self.lib.msb64_b200_ipc_close(ptr)
+
+    def route_peer(self, keys, rids, n, shift, bits, table, world, cursors, key_ptrs, rid_ptrs):
+        kp = (C.c_void_p * world)(*key_ptrs)
+        rp = (C.c_void_p * world)(*rid_ptrs)
+        _m._raise(self.lib.msb64_b200_route_peer(keys.data_ptr(), rids.data_ptr(), n, shift, bits,
+                                                 table.data_ptr(), world, cursors.data_ptr(), kp, rp,
+                                                 self._stream()))
+
     def sort(self, keys, rids, n, ws, ws_bytes, key_lo=0, key_hi=(1 << 64) - 1):
         _m._raise(self.lib.msb64_b200_sort_device_range(keys.data_ptr(), rids.data_ptr(), n, ws.data_ptr(),
                                                         ws_bytes, self._stream(), None, key_lo, key_hi))
@@ -107,7 +155,7 @@ class ShardedSorter:
     """Reusable buffers + the six steps above for `capacity` local pairs per rank."""
 
     def __init__(self, capacity: int, device=None, fudge: float = 1.125, bits: int = DEFAULT_BITS,
-                 group=None, ops=None):
+                 group=None, ops=None, exchange: str = "auto"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -129,8 +177,15 @@ class ShardedSorter:
         o = self.ops
         self.hist = o.empty(1 << self.bits)
         self.all_hist = o.empty(self.world << self.bits)
-        self.recv_keys = o.empty(self.recv_cap)
-        self.recv_rids = o.empty(self.recv_cap)
+        if exchange not in ("auto", "peer", "nccl"):
+            raise _m.Msb64Error(-2, "exchange must be 'auto', 'peer' or 'nccl'")
+        self.exchange = "nccl"
+        self._own = self._peer_keys = self._peer_rids = None
+        if self.world > 1 and exchange != "nccl" and getattr(o, "supports_peer", False):
+            self._setup_peer(exchange == "peer")
+        if self.exchange == "nccl":
+            self.recv_keys = o.empty(self.recv_cap)
+            self.recv_rids = o.empty(self.recv_cap)
         # the sort's scratch doubles as the send buffer: the exchange is over before the
         # local sort starts, and the sort treats its workspace as uninitialised
         self.ws, self.ws_bytes = o.workspace(self.recv_cap)
@@ -149,6 +204,63 @@ class ShardedSorter:
         else:
             caps.copy_(mine)
         self.recv_caps = caps.cpu().numpy().astype(np.int64)
+
+    # -- peer-memory exchange: map every rank's receive buffers into this process
+    def _setup_peer(self, required: bool):
+        torch, dist, o = self.torch, self.dist, self.ops
+        ok, opened = 1, []
+        try:
+            kp, self.recv_keys = o.alloc_exportable(self.recv_cap)
+            rp, self.recv_rids = o.alloc_exportable(self.recv_cap)
+            self._own = (kp, rp)
+            mine = torch.frombuffer(bytearray(o.ipc_export(kp) + o.ipc_export(rp)), dtype=torch.uint8)
+            handles = torch.empty(128 * self.world, dtype=torch.uint8, device=self.recv_keys.device)
+            dist.all_gather_into_tensor(handles, mine.to(handles.device), group=self.group)
+            h = handles.cpu().numpy().tobytes()
+            keys_p, rids_p = [0] * self.world, [0] * self.world
+            for r in range(self.world):
+                if r == self.rank:
+                    keys_p[r], rids_p[r] = kp, rp
+                    continue
+                a = o.ipc_open(h[128 * r: 128 * r + 64])
+                b = o.ipc_open(h[128 * r + 64: 128 * r + 128])
+                opened += [x for x in (a, b) if x]
+                if not a or not b:
+                    ok = 0
+                    break
+                keys_p[r], rids_p[r] = a, b
+        except _m.Msb64Error:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.hist.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()):
+            self.exchange = "peer"
+            self._peer_keys, self._peer_rids, self._opened = keys_p, rids_p, opened
+            self._done = torch.zeros(1, dtype=torch.int32, device=self.hist.device)
+            return
+        for x in opened:
+            o.ipc_close(x)
+        if self._own:
+            self.recv_keys = self.recv_rids = None
+            for x in self._own:
+                o.free_exportable(x)
+            self._own = None
+        if required:
+            raise _m.Msb64Error(-1, "peer-memory exchange unavailable (CUDA IPC / peer access failed)")
+
+    def close(self):
+        """Unmap the peers' buffers and release the exported ones (collective: every rank
+        must have finished using the sorter)."""
+        if self.exchange == "peer" and self._own:
+            self.torch.cuda.synchronize()
+            if self.world > 1:
+                self.dist.barrier(group=self.group)
+            for x in self._opened:
+                self.ops.ipc_close(x)
+            self.recv_keys = self.recv_rids = None
+            for x in self._own:
+                self.ops.free_exportable(x)
+            self._own = None
 
     # -- steps 1-3
     def plan(self, keys, n):
@@ -186,6 +298,16 @@ class ShardedSorter:
             # nothing to exchange: the receive buffer gets the pairs, the sort runs on it
             self.recv_keys[:n].copy_(keys[:n])
             self.recv_rids[:n].copy_(rids[:n])
+        elif self.exchange == "peer":
+            # steps 4 + 5 fused: this source's slice of destination d's buffer starts after
+            # the pairs of the lower-ranked sources.  The histogram all-gather above already
+            # told us that every rank has entered this call (nobody still reads its buffer).
+            starts = counts[: self.rank].sum(axis=0).astype(np.uint32)
+            cursors = self.ops.from_numpy(starts.view(np.int32))
+            table_d = self.ops.from_numpy(table)
+            self.ops.route_peer(keys, rids, n, self.shift, self.bits, table_d, self.world, cursors,
+                                self._peer_keys, self._peer_rids)
+            dist.all_reduce(self._done, group=self.group)      # every rank's stores have landed
         else:
             starts = np.concatenate([[0], np.cumsum(send)[:-1]]).astype(np.uint32)
             cursors = self.ops.from_numpy(starts.view(np.int32))

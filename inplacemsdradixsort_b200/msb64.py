@@ -39,7 +39,8 @@ EXPORTS = (
     "msb64_b200_host_free", "msb64_b200_device_alloc", "msb64_b200_device_free",
     "msb64_b200_memcpy_h2d", "msb64_b200_memcpy_d2h", "msb64_b200_memcpy_d2d",
     "msb64_b200_stream_sync", "msb64_b200_fill", "msb64_b200_check",
-    "msb64_b200_digit_histogram", "msb64_b200_route",
+    "msb64_b200_digit_histogram", "msb64_b200_route", "msb64_b200_route_peer",
+    "msb64_b200_ipc_export", "msb64_b200_ipc_open", "msb64_b200_ipc_close",
 )
 
 
@@ -119,6 +120,16 @@ def load_library() -> C.CDLL:
     L.msb64_b200_route.restype = C.c_int
     L.msb64_b200_route.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.msb64_b200_route_peer.restype = C.c_int
+    L.msb64_b200_route_peer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.c_void_p]
+    L.msb64_b200_ipc_export.restype = C.c_int
+    L.msb64_b200_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.msb64_b200_ipc_open.restype = C.c_void_p
+    L.msb64_b200_ipc_open.argtypes = [C.c_void_p]
+    L.msb64_b200_ipc_close.restype = C.c_int
+    L.msb64_b200_ipc_close.argtypes = [C.c_void_p]
     _lib = L
     return L
 

@@ -104,7 +104,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, kind, n, result):
+def _nccl_worker(rank, world, port, kind, n, exchange, result):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -116,19 +116,29 @@ def _nccl_worker(rank, world, port, kind, n, result):
         n_local = n + 1000 * rank
         keys = make(kind, n_local, seed=40 + rank)
         rids = np.arange(n_local, dtype=np.uint64) + np.uint64(rank << 40)
-        s = ShardedSorter(n_local, dev, fudge=1.3)
+        s = ShardedSorter(n_local, dev, fudge=1.3, exchange=exchange)
+        assert s.exchange == exchange
         ok_, or_, cnt = s.sort(torch.from_numpy(keys.view(np.int64)).to(dev),
                                torch.from_numpy(rids.view(np.int64)).to(dev))
         ordered = s.boundaries_ordered(ok_, cnt)
         torch.cuda.synchronize()
         result[rank] = (ok_.cpu().numpy().view(np.uint64).copy(), or_.cpu().numpy().view(np.uint64).copy(),
                         keys, rids, ordered)
+        # a second sort through the same buffers (peers write into them again)
+        keys2 = make(kind, n_local, seed=400 + rank)
+        ok2, or2, cnt2 = s.sort(torch.from_numpy(keys2.view(np.int64)).to(dev),
+                                torch.from_numpy(rids.view(np.int64)).to(dev))
+        assert s.boundaries_ordered(ok2, cnt2)
+        k2 = ok2.cpu().numpy().view(np.uint64)
+        assert bool(np.all(k2[:-1] <= k2[1:]))
+        s.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("kind", ["uniform", "sorted"])
-def test_sharded_sorter_two_gpus_nccl(gpu, kind):
+def test_sharded_sorter_two_gpus_nccl(gpu, kind, exchange):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -136,7 +146,7 @@ def test_sharded_sorter_two_gpus_nccl(gpu, kind):
     world = 2
     mgr = mp.Manager()
     result = mgr.dict()
-    mp.spawn(_nccl_worker, args=(world, _free_port(), kind, 1_000_003, result), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, _free_port(), kind, 1_000_003, exchange, result), nprocs=world, join=True)
     res = [result[r] for r in range(world)]
     all_k = np.concatenate([r[2] for r in res])
     all_r = np.concatenate([r[3] for r in res])
