@@ -334,6 +334,28 @@ def main_b200(args):
         "clocks": clocks, "gpu_launches": launches, "verified": True,
     }
 
+    # ---- N > 1: device times of the sharded steps; the exchange against NVLink bandwidth
+    if sorter is not None:
+        restore()
+        barrier()
+        sorter.sort(keys, rids, timed=True)
+        lt = sorter.last_times
+        tt = torch.tensor([lt["plan"], lt["exchange"], lt["barrier"], lt["local_sort"]],
+                          dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sent = torch.tensor([lt["pairs_sent_to_peers"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(sent, op=dist.ReduceOp.MAX)
+        ex_ms = float(tt[1] + tt[2])
+        gbs = 16 * int(sent.item()) / (ex_ms * 1e-3) / 1e9 if ex_ms > 0 else None
+        line["exchange"] = {
+            "kind": sorter.exchange, "plan_ms": float(tt[0]), "exchange_ms": float(tt[1]),
+            "barrier_ms": float(tt[2]), "local_sort_ms": float(tt[3]),
+            "bytes_out_per_gpu": 16 * int(sent.item()), "out_GB/s_per_gpu": gbs,
+            "nvlink_peak_GB/s_per_direction": 900.0,
+            "frac_of_nvlink": gbs / 900.0 if gbs else None,
+            "note": "max over ranks; exchange = routing kernel (+ all-to-all for nccl) + completion barrier",
+        }
+
     # ---- roofline of the dominant kernel, from CUDA events inside this process
     if rank == 0 or dist is None:
         restore()

@@ -25,8 +25,8 @@
 #include "msb64_histogram.cuh"
 #include "msb64_local_sort.cuh"
 #include "msb64_plan.cuh"
-#include "msb64_route.cuh"
 #include "msb64_scatter.cuh"
+#include "msb64_route.cuh"
 
 using namespace msb64;
 
@@ -713,7 +713,7 @@ static int route_common(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t
 					      int(route_smem(ROUTE_MAX_BITS))));
 		configured = true;
 	}
-	route_kernel<<<g_dev.sms * 2, ROUTE_THREADS, route_smem(bits), static_cast<cudaStream_t>(stream)>>>(
+	route_kernel<<<g_dev.sms * 3, ROUTE_THREADS, route_smem(bits), static_cast<cudaStream_t>(stream)>>>(
 		d_keys, d_rids, uint32_t(n), shift, bits, d_bin_to_dest, ndest, d_cursors, dst);
 	g_launches += 1;
 	CUDA_TRY(cudaGetLastError());

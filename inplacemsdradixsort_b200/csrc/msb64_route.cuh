@@ -18,6 +18,7 @@
 //                           and NVLink run at full rate.
 #pragma once
 #include "msb64_common.cuh"
+#include "msb64_scatter.cuh"   // bulk-copy / mbarrier primitives, tile_ranks
 
 namespace msb64 {
 
@@ -51,60 +52,90 @@ struct RouteDst {
 	uint64_t *rids[ROUTE_MAX_DEST];
 };
 
+constexpr size_t ROUTE_SMEM = size_t(TILE) * 16                         // keys + rids of the tile (bulk-copied)
+			      + size_t(TILE) * 2                        // source slot by destination-ordered position
+			      + (ROUTE_MAX_DEST + 32) * 4               // per-destination counters (+ dummies)
+			      + 2 * ROUTE_MAX_DEST * 4                  // local base, global - local base
+			      + 2 * ROUTE_MAX_DEST * 8                  // output pointers
+			      + 16;                                     // mbarrier
+
 // cursors[d] = next free slot of this source in destination d's output arrays (initialised
 // by the host: exclusive prefix of the send counts for a local send buffer, number of pairs
 // the lower-ranked sources send to d for a peer's receive buffer).
-__global__ void __launch_bounds__(ROUTE_THREADS, 2)
+//
+// Same structure as scatter_kernel (msb64_scatter.cuh): the tile lands in shared memory by
+// bulk asynchronous copies, the pairs stay where they landed, a 2-byte source slot per pair
+// is written in destination order and the write-out gathers through it; three blocks per SM
+// keep enough stores in flight for NVLink (tools/p2p_bench.cu: plain coalesced 8-byte stores
+// reach 0.69 TB/s per direction with >= 4 x 256 threads per SM, copy engines 0.78 TB/s).
+// The bin -> destination table (4 KiB at 12 bits) is read through L1.
+__global__ void __launch_bounds__(ROUTE_THREADS, 3)
 route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, int bits,
-	     const uint8_t *bin_to_dest, int ndest, uint32_t *cursors, const RouteDst dst)
+	     const uint8_t *__restrict__ bin_to_dest, int ndest, uint32_t *cursors, const RouteDst dst)
 {
-	constexpr int THREADS = ROUTE_THREADS, ITEMS = ROUTE_ITEMS;
+	constexpr int THREADS = ROUTE_THREADS, ITEMS = ROUTE_ITEMS, ND = ROUTE_MAX_DEST;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	uint64_t *skeys = reinterpret_cast<uint64_t *>(smem_raw);             // [TILE]
-	uint64_t *srids = skeys + TILE;                                       // [TILE]
-	uint32_t *cnt = reinterpret_cast<uint32_t *>(srids + TILE);           // [ROUTE_MAX_DEST + 32]
-	uint32_t *lbase = cnt + ROUTE_MAX_DEST + 32;                          // [ROUTE_MAX_DEST]
-	uint32_t *delta = lbase + ROUTE_MAX_DEST;                             // [ROUTE_MAX_DEST]
-	uint64_t **okeys = reinterpret_cast<uint64_t **>(delta + ROUTE_MAX_DEST);   // [ROUTE_MAX_DEST]
-	uint64_t **orids = okeys + ROUTE_MAX_DEST;                             // [ROUTE_MAX_DEST]
-	uint8_t *table = reinterpret_cast<uint8_t *>(orids + ROUTE_MAX_DEST); // [1 << bits]
+	uint64_t *kin = reinterpret_cast<uint64_t *>(smem_raw);               // [TILE]
+	uint64_t *rin = kin + TILE;                                           // [TILE]
+	uint16_t *sidx = reinterpret_cast<uint16_t *>(rin + TILE);            // [TILE]
+	uint32_t *cnt = reinterpret_cast<uint32_t *>(sidx + TILE);            // [ND + 32]
+	uint32_t *lbase = cnt + ND + 32;                                      // [ND]
+	uint32_t *delta = lbase + ND;                                         // [ND]
+	uint64_t **okeys = reinterpret_cast<uint64_t **>(delta + ND);         // [ND]
+	uint64_t **orids = okeys + ND;                                        // [ND]
+	uint64_t *bar = reinterpret_cast<uint64_t *>(orids + ND);
 
 	const uint32_t tid = threadIdx.x, lane = lane_id();
-	const uint32_t nb = 1u << bits;
-	for (uint32_t i = tid; i < nb; i += THREADS) table[i] = bin_to_dest[i];
+	const uint32_t dmask = (1u << bits) - 1;
+	const uint32_t ntiles = (n + TILE - 1) / TILE;
+	if (blockIdx.x >= ntiles) return;
+	// thread 0: a tile that lies inside the array completely is fetched by bulk copies
+	auto start_copy = [&](uint32_t t) {
+		if (t >= ntiles || (t + 1) * uint64_t(TILE) > n) return;
+		mbar_expect_tx(bar, TILE * 16);
+		bulk_copy_g2s(kin, keys + size_t(t) * TILE, TILE * 8, bar);
+		bulk_copy_g2s(rin, rids + size_t(t) * TILE, TILE * 8, bar);
+	};
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		start_copy(blockIdx.x);
+	}
 	if (tid < uint32_t(ndest)) {
 		okeys[tid] = dst.keys[tid];
 		orids[tid] = dst.rids[tid];
 	}
-	const uint32_t ntiles = (n + TILE - 1) / TILE;
+	for (uint32_t i = tid; i < ND + 32; i += THREADS) cnt[i] = 0;
+	__syncthreads();
 
+	uint32_t parity = 0;
 	for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
 		const uint32_t lo = t * TILE;
 		const uint32_t count = min(TILE, n - lo);
-		for (uint32_t i = tid; i < ROUTE_MAX_DEST + 32; i += THREADS) cnt[i] = 0;
-		__syncthreads();
-
-		uint64_t k[ITEMS], r[ITEMS];
-		uint32_t rank[ITEMS], dest[ITEMS];
-#pragma unroll
-		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			k[j] = i < count ? ld_stream_u64(keys + lo + i) : 0;
+		if (count == TILE) {
+			mbar_wait(bar, parity);
+			parity ^= 1u;
+		} else {
+			// the array's tail: plain loads
+			for (uint32_t i = tid; i < count; i += THREADS) {
+				kin[i] = ld_stream_u64(keys + lo + i);
+				rin[i] = ld_stream_u64(rids + lo + i);
+			}
+			__syncthreads();
 		}
+		// destination of every pair, rank among the tile's pairs with the same destination
+		// (slots past the end count into per-lane dummy counters)
+		uint32_t dr[ITEMS];
+		{
+			const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(kin);
 #pragma unroll
-		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			r[j] = i < count ? ld_stream_u64(rids + lo + i) : 0;
+			for (int jj = 0; jj < ITEMS / 2; ++jj) {
+				const ulonglong2 v = k2[jj * THREADS + tid];
+				const uint32_t s0 = (jj * THREADS + tid) * 2;
+				dr[2 * jj] = s0 < count ? uint32_t(__ldg(bin_to_dest + (uint32_t(v.x >> shift) & dmask))) : ND + lane;
+				dr[2 * jj + 1] = s0 + 1 < count ? uint32_t(__ldg(bin_to_dest + (uint32_t(v.y >> shift) & dmask))) : ND + lane;
+			}
 		}
-		// branch-free ranking (see tile_ranks in msb64_scatter.cuh); slots past the end of
-		// the slice count into per-lane dummy bins
-#pragma unroll
-		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			dest[j] = i < count ? uint32_t(table[uint32_t(k[j] >> shift) & (nb - 1)])
-					    : uint32_t(ROUTE_MAX_DEST) + lane;
-			rank[j] = atomicAdd(&cnt[dest[j]], 1u);
-		}
+		tile_ranks<ITEMS, ND>(cnt, dr);
 		__syncthreads();
 		if (tid < uint32_t(ndest)) {
 			// at most 64 destinations: every owner thread sums its predecessors
@@ -118,29 +149,26 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 		__syncthreads();
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j) {
-			const uint32_t i = j * THREADS + tid;
-			if (i < count) {
-				const uint32_t p = lbase[dest[j]] + rank[j];
-				skeys[p] = k[j];
-				srids[p] = r[j];
-			}
+			const uint32_t d = dr[j] >> RANK_BITS;
+			if (d < ND) sidx[lbase[d] + (dr[j] & RANK_MASK)] = uint16_t(((j >> 1) * THREADS + tid) * 2 + (j & 1));
 		}
 		__syncthreads();
+#pragma unroll 4
 		for (uint32_t i = tid; i < count; i += THREADS) {
-			const uint64_t key = skeys[i];
-			const uint32_t d = table[uint32_t(key >> shift) & (nb - 1)];
+			const uint32_t s = sidx[i];
+			const uint64_t key = kin[s];
+			const uint64_t rid = rin[s];
+			const uint32_t d = __ldg(bin_to_dest + (uint32_t(key >> shift) & dmask));
 			const uint32_t at = delta[d] + i;
 			st_stream_u64(okeys[d] + at, key);
-			st_stream_u64(orids[d] + at, srids[i]);
+			st_stream_u64(orids[d] + at, rid);
 		}
+		for (uint32_t i = tid; i < ND + 32; i += THREADS) cnt[i] = 0;
 		__syncthreads();
+		if (tid == 0) start_copy(t + gridDim.x);
 	}
 }
 
-constexpr size_t route_smem(int bits)
-{
-	return size_t(TILE) * 16 + (ROUTE_MAX_DEST + 32 + 2 * ROUTE_MAX_DEST) * 4 + 2 * ROUTE_MAX_DEST * 8
-	       + (size_t(1) << bits);
-}
+constexpr size_t route_smem(int) { return ROUTE_SMEM; }
 
 } // namespace msb64

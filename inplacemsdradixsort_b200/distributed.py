@@ -276,15 +276,23 @@ class ShardedSorter:
         counts = exchange_counts(h, table, self.world)
         return table, counts
 
-    def sort(self, keys, rids, n: int | None = None):
+    def sort(self, keys, rids, n: int | None = None, timed: bool = False):
         """keys, rids: this rank's pairs (8-byte integer tensors on the sorter's device).
         Returns (keys, rids, count) of this rank's key range, sorted; the tensors are
-        views of the sorter's receive buffers, valid until the next call."""
+        views of the sorter's receive buffers, valid until the next call.
+        timed=True (CUDA ops only) records device times of the steps in self.last_times
+        (milliseconds: plan, exchange, barrier, local_sort) and synchronises."""
         torch, dist = self.torch, self.dist
+        ev = None
+        if timed:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
         n = keys.numel() if n is None else int(n)
         if n > self.capacity:
             raise _m.Msb64Error(-2, f"{n} pairs exceed the sorter's capacity {self.capacity}")
         table, counts = self.plan(keys, n)
+        if ev:
+            ev[1].record()
         self.last_counts = counts
         send = counts[self.rank]
         recv = counts[:, self.rank]
@@ -307,6 +315,8 @@ class ShardedSorter:
             table_d = self.ops.from_numpy(table)
             self.ops.route_peer(keys, rids, n, self.shift, self.bits, table_d, self.world, cursors,
                                 self._peer_keys, self._peer_rids)
+            if ev:
+                ev[2].record()
             dist.all_reduce(self._done, group=self.group)      # every rank's stores have landed
         else:
             starts = np.concatenate([[0], np.cumsum(send)[:-1]]).astype(np.uint32)
@@ -325,7 +335,18 @@ class ShardedSorter:
             key_hi = ((int(mine[-1]) + 1) << self.shift) - 1
         else:
             key_lo, key_hi = 0, (1 << 64) - 1
+        if ev:
+            if self.exchange != "peer" or self.world == 1:
+                ev[2].record()
+            ev[3].record()
         self.ops.sort(self.recv_keys, self.recv_rids, total, self.ws, self.ws_bytes, key_lo, key_hi)
+        if ev:
+            ev[4].record()
+            torch.cuda.synchronize()
+            self.last_times = {"plan": ev[0].elapsed_time(ev[1]), "exchange": ev[1].elapsed_time(ev[2]),
+                               "barrier": ev[2].elapsed_time(ev[3]), "local_sort": ev[3].elapsed_time(ev[4]),
+                               "pairs_sent_to_peers": int(send.sum() - send[self.rank]),
+                               "pairs_received": total}
         return self.recv_keys[:total], self.recv_rids[:total], total
 
     # -- acceptance across ranks (the cross-node half of check(), msb_64.c:2485-2495)

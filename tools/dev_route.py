@@ -1,0 +1,47 @@
+"""Developer timing of the routing kernel alone (local output): n pairs, ndest destinations."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import inplacemsdradixsort_b200 as m
+
+n = int(eval(sys.argv[1])) if len(sys.argv) > 1 else 1 << 28
+lib = m.load_library()
+dev = torch.device("cuda", 0)
+k = torch.empty(n, dtype=torch.int64, device=dev)
+r = torch.empty(n, dtype=torch.int64, device=dev)
+ok, orr = torch.empty_like(k), torch.empty_like(r)
+st = torch.cuda.current_stream().cuda_stream
+lib.msb64_b200_fill(k.data_ptr(), r.data_ptr(), n, 0, 1, 0, st)
+hist = torch.zeros(4096, dtype=torch.int64, device=dev)
+lib.msb64_b200_digit_histogram(k.data_ptr(), n, 52, 12, hist.data_ptr(), st)
+h = hist.cpu().numpy()
+for ndest in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["1", "2", "4", "8", "64"])]:
+    table = (np.arange(4096) * ndest // 4096).astype(np.uint8)
+    counts = np.bincount(table, weights=h, minlength=ndest).astype(np.int64)
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.uint32)
+    td = torch.from_numpy(table).to(dev)
+    best = 1e9
+    for it in range(4):
+        cur = torch.from_numpy(starts.view(np.int32).copy()).to(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = lib.msb64_b200_route(k.data_ptr(), r.data_ptr(), n, 52, 12, td.data_ptr(), ndest, cur.data_ptr(),
+                                  ok.data_ptr(), orr.data_ptr(), st)
+        b.record()
+        torch.cuda.synchronize()
+        assert rc == 0
+        best = min(best, a.elapsed_time(b))
+    # check: destination d's slice holds exactly its keys (multiset by sum) and only them
+    okk = ok.cpu().numpy().view(np.uint64) if n <= (1 << 26) else None
+    good = True
+    if okk is not None:
+        dig = (okk >> np.uint64(52)).astype(np.int64)
+        for d in range(ndest):
+            sl = table[dig[int(starts[d]): int(starts[d] + counts[d])]]
+            good &= bool(np.all(sl == d))
+    print(f"ndest {ndest:3d}: {best:7.3f} ms  {32 * n / best / 1e6:8.1f} GB/s  ok={good}")
