@@ -709,12 +709,19 @@ static int route_common(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t
 	if (!n) return MSB64_OK;
 	static bool configured = false;
 	if (!configured) {
-		CUDA_TRY(cudaFuncSetAttribute(route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-					      int(route_smem(ROUTE_MAX_BITS))));
+		CUDA_TRY(cudaFuncSetAttribute(route_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					      int(RouteCfg<16>::SMEM)));
+		CUDA_TRY(cudaFuncSetAttribute(route_kernel<ROUTE_MAX_DEST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					      int(RouteCfg<ROUTE_MAX_DEST>::SMEM)));
 		configured = true;
 	}
-	route_kernel<<<g_dev.sms * 3, ROUTE_THREADS, route_smem(bits), static_cast<cudaStream_t>(stream)>>>(
-		d_keys, d_rids, uint32_t(n), shift, bits, d_bin_to_dest, ndest, d_cursors, dst);
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (ndest <= 16)
+		route_kernel<16><<<g_dev.sms * 3, ROUTE_THREADS, RouteCfg<16>::SMEM, st>>>(
+			d_keys, d_rids, uint32_t(n), shift, bits, d_bin_to_dest, ndest, d_cursors, dst);
+	else
+		route_kernel<ROUTE_MAX_DEST><<<g_dev.sms * 2, ROUTE_THREADS, RouteCfg<ROUTE_MAX_DEST>::SMEM, st>>>(
+			d_keys, d_rids, uint32_t(n), shift, bits, d_bin_to_dest, ndest, d_cursors, dst);
 	g_launches += 1;
 	CUDA_TRY(cudaGetLastError());
 	return MSB64_OK;

@@ -52,12 +52,18 @@ struct RouteDst {
 	uint64_t *rids[ROUTE_MAX_DEST];
 };
 
-constexpr size_t ROUTE_SMEM = size_t(TILE) * 16                         // keys + rids of the tile (bulk-copied)
-			      + size_t(TILE) * 2                        // source slot by destination-ordered position
-			      + (ROUTE_MAX_DEST + 32) * 4               // per-destination counters (+ dummies)
-			      + 2 * ROUTE_MAX_DEST * 4                  // local base, global - local base
-			      + 2 * ROUTE_MAX_DEST * 8                  // output pointers
-			      + 16;                                     // mbarrier
+constexpr uint32_t ROUTE_ALIGN = 16;     // pairs: every destination's run is written in 128-byte aligned pieces
+
+template <int ND>
+struct RouteCfg {
+	static constexpr uint32_t SLOTS = TILE + ROUTE_ALIGN * ND;              // padded destination-ordered positions
+	static constexpr size_t SMEM = size_t(TILE) * 16                        // keys + rids of the tile (bulk-copied)
+				       + size_t(SLOTS) * 2                      // source slot by padded position
+				       + (ND + 32) * 4                          // per-destination counters (+ dummies)
+				       + 3 * ND * 4                             // padded size, local base, global - local base
+				       + 2 * ND * 8                             // output pointers
+				       + 16;                                    // mbarrier
+};
 
 // cursors[d] = next free slot of this source in destination d's output arrays (initialised
 // by the host: exclusive prefix of the send counts for a local send buffer, number of pairs
@@ -66,24 +72,32 @@ constexpr size_t ROUTE_SMEM = size_t(TILE) * 16                         // keys 
 // Same structure as scatter_kernel (msb64_scatter.cuh): the tile lands in shared memory by
 // bulk asynchronous copies, the pairs stay where they landed, a 2-byte source slot per pair
 // is written in destination order and the write-out gathers through it; three blocks per SM
-// keep enough stores in flight for NVLink (tools/p2p_bench.cu: plain coalesced 8-byte stores
-// reach 0.69 TB/s per direction with >= 4 x 256 threads per SM, copy engines 0.78 TB/s).
+// (ND = 16) keep enough stores in flight for NVLink (tools/p2p_bench.cu: plain coalesced
+// 8-byte stores reach 0.69 TB/s per direction with >= 4 x 256 threads per SM, copy engines
+// 0.78 TB/s).  Stores to a peer are not merged by any cache on the way, so the write-out is
+// laid out in GLOBAL 128-byte lines: the destination-ordered positions are padded so that
+// position p of destination d goes to element delta[d] + p with delta[d] a multiple of 16 --
+// every warp store is two whole lines instead of a line and two fragments.
 // The bin -> destination table (4 KiB at 12 bits) is read through L1.
-__global__ void __launch_bounds__(ROUTE_THREADS, 3)
+template <int ND>
+__global__ void __launch_bounds__(ROUTE_THREADS, ND <= 16 ? 3 : 2)
 route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, int bits,
 	     const uint8_t *__restrict__ bin_to_dest, int ndest, uint32_t *cursors, const RouteDst dst)
 {
-	constexpr int THREADS = ROUTE_THREADS, ITEMS = ROUTE_ITEMS, ND = ROUTE_MAX_DEST;
+	constexpr int THREADS = ROUTE_THREADS, ITEMS = ROUTE_ITEMS;
+	using Cfg = RouteCfg<ND>;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint64_t *kin = reinterpret_cast<uint64_t *>(smem_raw);               // [TILE]
 	uint64_t *rin = kin + TILE;                                           // [TILE]
-	uint16_t *sidx = reinterpret_cast<uint16_t *>(rin + TILE);            // [TILE]
-	uint32_t *cnt = reinterpret_cast<uint32_t *>(sidx + TILE);            // [ND + 32]
-	uint32_t *lbase = cnt + ND + 32;                                      // [ND]
-	uint32_t *delta = lbase + ND;                                         // [ND]
+	uint16_t *sidx = reinterpret_cast<uint16_t *>(rin + TILE);            // [SLOTS]
+	uint32_t *cnt = reinterpret_cast<uint32_t *>(sidx + Cfg::SLOTS);      // [ND + 32]
+	uint32_t *psize = cnt + ND + 32;                                      // [ND] padded run length
+	uint32_t *lbase = psize + ND;                                         // [ND] first position of the run
+	uint32_t *delta = lbase + ND;                                         // [ND] global element - position
 	uint64_t **okeys = reinterpret_cast<uint64_t **>(delta + ND);         // [ND]
 	uint64_t **orids = okeys + ND;                                        // [ND]
 	uint64_t *bar = reinterpret_cast<uint64_t *>(orids + ND);
+	__shared__ uint32_t s_slots;
 
 	const uint32_t tid = threadIdx.x, lane = lane_id();
 	const uint32_t dmask = (1u << bits) - 1;
@@ -137,14 +151,25 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 		}
 		tile_ranks<ITEMS, ND>(cnt, dr);
 		__syncthreads();
+		// every destination's owner thread claims the run's slice of the output and pads
+		// the run to the output's 128-byte lines
+		uint32_t g = 0, c = 0, head = 0;
 		if (tid < uint32_t(ndest)) {
-			// at most 64 destinations: every owner thread sums its predecessors
+			c = cnt[tid];
+			g = c ? atomicAdd(&cursors[tid], c) : 0;
+			head = c ? (g & (ROUTE_ALIGN - 1)) : 0;
+			psize[tid] = (head + c + ROUTE_ALIGN - 1) & ~(ROUTE_ALIGN - 1);
+		}
+		__syncthreads();
+		if (tid < uint32_t(ndest)) {
 			uint32_t before = 0;
-			for (uint32_t d = 0; d < tid; ++d) before += cnt[d];
-			const uint32_t c = cnt[tid];
-			const uint32_t g = c ? atomicAdd(&cursors[tid], c) : 0;
-			lbase[tid] = before;
-			delta[tid] = g - before;
+			for (uint32_t d = 0; d < tid; ++d) before += psize[d];
+			const uint32_t first = before + head;
+			lbase[tid] = first;
+			delta[tid] = g - first;
+			for (uint32_t p = before; p < first; ++p) sidx[p] = 0xffffu;            // padding in front
+			for (uint32_t p = first + c; p < before + psize[tid]; ++p) sidx[p] = 0xffffu;   // and behind
+			if (tid + 1 == uint32_t(ndest)) s_slots = before + psize[tid];
 		}
 		__syncthreads();
 #pragma unroll
@@ -153,22 +178,23 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 			if (d < ND) sidx[lbase[d] + (dr[j] & RANK_MASK)] = uint16_t(((j >> 1) * THREADS + tid) * 2 + (j & 1));
 		}
 		__syncthreads();
+		const uint32_t slots = s_slots;
 #pragma unroll 4
-		for (uint32_t i = tid; i < count; i += THREADS) {
-			const uint32_t s = sidx[i];
-			const uint64_t key = kin[s];
-			const uint64_t rid = rin[s];
-			const uint32_t d = __ldg(bin_to_dest + (uint32_t(key >> shift) & dmask));
-			const uint32_t at = delta[d] + i;
-			st_stream_u64(okeys[d] + at, key);
-			st_stream_u64(orids[d] + at, rid);
+		for (uint32_t p = tid; p < slots; p += THREADS) {
+			const uint32_t s = sidx[p];
+			if (s != 0xffffu) {
+				const uint64_t key = kin[s];
+				const uint64_t rid = rin[s];
+				const uint32_t d = __ldg(bin_to_dest + (uint32_t(key >> shift) & dmask));
+				const uint32_t at = delta[d] + p;
+				st_stream_u64(okeys[d] + at, key);
+				st_stream_u64(orids[d] + at, rid);
+			}
 		}
 		for (uint32_t i = tid; i < ND + 32; i += THREADS) cnt[i] = 0;
 		__syncthreads();
 		if (tid == 0) start_copy(t + gridDim.x);
 	}
 }
-
-constexpr size_t route_smem(int) { return ROUTE_SMEM; }
 
 } // namespace msb64
