@@ -67,6 +67,7 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------ schedule
 std::vector<int> g_schedule_override;
+const bool g_no_fuse = getenv("MSB64_NO_FUSE") != nullptr;     // developer switch: separate histogram pass per level
 
 // Digit widths, most significant first (the role of schedule_passes, msb_64.c:1334), for
 // keys of which only the low `width` bits vary (64 when nothing is known about the keys).
@@ -138,6 +139,7 @@ struct Device {
 	bool ready = false;
 	int sms = 0;
 	int hist_blocks[MAX_BITS + 1] = {0};      // resident blocks per SM, by digit width
+	int fused_blocks[MAX_BITS + 1] = {0};     // same for the fused (two-level) histogram
 	int scatter_blocks[MAX_BITS + 1] = {0};
 	int local_blocks = 0;
 	// cached allocations (grow-only)
@@ -160,12 +162,20 @@ int setup_bits()
 {
 	using H = HistCfg<BITS, 256>;
 	using S = ScatterCfg<BITS, SCATTER_THREADS>;
-	CUDA_TRY(cudaFuncSetAttribute(histogram_kernel<BITS, 256>,
+	CUDA_TRY(cudaFuncSetAttribute(histogram_kernel<BITS, 256, false>,
 				      cudaFuncAttributeMaxDynamicSharedMemorySize, int(H::SMEM)));
+	if (BITS < FUSE_MAX_BITS - 3) {
+		CUDA_TRY(cudaFuncSetAttribute(histogram_kernel<BITS, 256, true>,
+					      cudaFuncAttributeMaxDynamicSharedMemorySize,
+					      int(H::SMEM + (size_t(H::NB + 32) << (FUSE_MAX_BITS - BITS)) * 4)));
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+			&g_dev.fused_blocks[BITS], histogram_kernel<BITS, 256, true>, 256,
+			H::SMEM + (size_t(H::NB + 32) << (FUSE_MAX_BITS - BITS)) * 4));
+	}
 	CUDA_TRY(cudaFuncSetAttribute(scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB>,
 				      cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::SMEM)));
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-		&g_dev.hist_blocks[BITS], histogram_kernel<BITS, 256>, 256, H::SMEM));
+		&g_dev.hist_blocks[BITS], histogram_kernel<BITS, 256, false>, 256, H::SMEM));
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
 		&g_dev.scatter_blocks[BITS], scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB>, SCATTER_THREADS, S::SMEM));
 	if (g_dev.hist_blocks[BITS] < 1 || g_dev.scatter_blocks[BITS] < 1)
@@ -213,7 +223,7 @@ int ensure_events()
 
 // ------------------------------------------------------------------ workspace
 struct Layout {
-	size_t keys_b, rids_b, segs[2], tiles[2], hist[2], units, copies, ctl, total;
+	size_t keys_b, rids_b, segs[2], tiles[2], hist[2], units, copies, ctl, fused, total;
 	uint32_t max_segs, max_tiles, max_units, max_copies;
 };
 
@@ -237,6 +247,7 @@ Layout make_layout(uint64_t n, const std::vector<int> &sched)
 	L.units = take(size_t(L.max_units) * sizeof(Unit));
 	L.copies = take(size_t(L.max_copies) * sizeof(CopyTile));
 	L.ctl = take(sizeof(Control));
+	L.fused = take((size_t(1) << FUSE_MAX_BITS) * 4);
 	L.total = at;
 	return L;
 }
@@ -249,9 +260,20 @@ void launch_level(const Ctx &c, int level, int shift, uint32_t origin, int next_
 	using H = HistCfg<BITS, 256>;
 	using S = ScatterCfg<BITS, SCATTER_THREADS>;
 	if (ev) cudaEventRecord(ev[0], st);
-	histogram_kernel<BITS, 256><<<g_dev.sms * g_dev.hist_blocks[BITS], 256, H::SMEM, st>>>(c, level, shift, origin);
+	// level 0 is one segment: its histogram pass also counts the level-1 digits per bin
+	// (32 KiB of shared counters), and level 1 needs no histogram pass
+	const bool fuse = level == 0 && next_bits > 0 && BITS + next_bits <= FUSE_MAX_BITS &&
+			  BITS < FUSE_MAX_BITS - 3 && g_dev.fused_blocks[BITS] > 0 && shift >= next_bits && !g_no_fuse;
+	if (fuse) {
+		const size_t smem = H::SMEM + (size_t(H::NB + 32) << next_bits) * 4;
+		histogram_kernel<BITS, 256, true><<<g_dev.sms * g_dev.fused_blocks[BITS], 256, smem, st>>>(
+			c, level, shift, origin, shift - next_bits, next_bits);
+	} else {
+		histogram_kernel<BITS, 256, false><<<g_dev.sms * g_dev.hist_blocks[BITS], 256, H::SMEM, st>>>(
+			c, level, shift, origin, 0, 0);
+	}
 	if (ev) cudaEventRecord(ev[1], st);
-	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits, shift);
+	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits, shift, fuse);
 	if (ev) cudaEventRecord(ev[2], st);
 	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<g_dev.sms * g_dev.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, shift, origin);
 	if (ev) cudaEventRecord(ev[3], st);
@@ -299,6 +321,7 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	c.units = reinterpret_cast<Unit *>(w + L.units);
 	c.copies = reinterpret_cast<CopyTile *>(w + L.copies);
 	c.ctl = reinterpret_cast<Control *>(w + L.ctl);
+	c.fused = reinterpret_cast<uint32_t *>(w + L.fused);
 	c.n = uint32_t(n);
 	c.max_segs = L.max_segs;
 	c.max_tiles = L.max_tiles;

@@ -29,13 +29,16 @@ constexpr int MAX_BITS = 11;            // widest digit a level may use
 constexpr uint32_t LOCAL_CAP = MSB64_LOCAL_CAP;   // pairs the local sort holds in shared memory
 constexpr uint32_t TILE = 4096;         // element slots per histogram/scatter tile
 constexpr uint32_t COPY_TILE = 8192;    // pairs per copy tile
+constexpr int FUSE_MAX_BITS = 13;       // level 0 + level 1 digit bits the fused histogram pass handles (32 KiB of counters)
 
 struct Seg {
 	uint32_t begin;   // first element
 	uint32_t size;    // > LOCAL_CAP by construction
 	uint32_t buf;     // buffer holding it now (0 = A, 1 = B)
-	uint32_t skip;    // set by plan: every key has the same digit, nothing to move
+	uint32_t skip;    // SEG_SKIP: every key has the same digit, nothing to move (set by this level's plan);
+	                  // SEG_HIST_READY: the histogram was computed by the level above (fused pass)
 };
+constexpr uint32_t SEG_SKIP = 1u, SEG_HIST_READY = 2u;
 
 struct Tile {
 	uint32_t seg;     // index into this level's Seg list
@@ -88,6 +91,7 @@ struct Ctx {
 	Unit *units;
 	CopyTile *copies;
 	Control *ctl;
+	uint32_t *fused;         // [2^bits0][2^bits1] level-1 digit counts per level-0 bin (fused histogram pass)
 	uint32_t n;
 	uint32_t max_segs, max_tiles, max_units, max_copies;
 };

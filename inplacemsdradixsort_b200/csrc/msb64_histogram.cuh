@@ -27,9 +27,11 @@ struct HistCfg {
 // branch in front of a shared atomic makes ptxas re-materialise the shared-window base,
 // S2UR SR_CgaCtaId, per atomic); a warp whose ITEMS x 32 digits are all equal (presorted
 // or low-entropy input) adds once instead of serialising on one address.
-template <int ITEMS, int NB>
+// FUSE: also count the next level's digit per bin of this level (table h2, [NB][2^fbits]).
+template <int ITEMS, int NB, bool FUSE>
 __device__ __forceinline__ void hist_add_tile(uint32_t *h, const uint64_t (&k)[ITEMS], int shift,
-					      uint32_t origin, uint32_t validmask)
+					      uint32_t origin, uint32_t validmask, uint32_t *h2 = nullptr,
+					      int fshift = 0, int fbits = 0)
 {
 	// keys outside the segment count into a per-lane dummy bin behind the real ones
 	uint32_t d[ITEMS];
@@ -46,17 +48,29 @@ __device__ __forceinline__ void hist_add_tile(uint32_t *h, const uint64_t (&k)[I
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j) atomicAdd(&h[d[j]], 1u);
 	}
+	if (FUSE) {
+		// invalid items (digit >= NB) land in the dummy rows behind the table
+		const uint32_t fmask = (1u << fbits) - 1;
+#pragma unroll
+		for (int j = 0; j < ITEMS; ++j)
+			atomicAdd(&h2[(d[j] << fbits) | (uint32_t(k[j] >> fshift) & fmask)], 1u);
+	}
 }
 
-template <int BITS, int THREADS>
+// FUSE (level 0 only, one segment): fshift / fbits describe the level-1 digit; the counts of
+// level-1 digits per level-0 bin go to c.fused and become the children's histograms in the
+// plan kernel, so level 1 needs no histogram pass of its own.
+template <int BITS, int THREADS, bool FUSE>
 __global__ void __launch_bounds__(THREADS)
-histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t origin)
+histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t origin,
+		 const int fshift, const int fbits)
 {
 	using Cfg = HistCfg<BITS, THREADS>;
 	constexpr int NB = Cfg::NB, ITEMS = Cfg::ITEMS;
 	static_assert(ITEMS % 2 == 0, "tile is loaded as 16-byte pairs");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);     // [NB]
+	uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);     // [NB + 32]
+	uint32_t *sh2 = sh + NB + 32;                              // FUSE: [(NB + 32) << fbits] (dummy rows included)
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ntiles = c.ctl->ntiles[level];
@@ -65,6 +79,8 @@ histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t o
 	uint32_t *hist = (level & 1) ? c.hist[1] : c.hist[0];
 
 	for (int i = tid; i < NB + 32; i += THREADS) sh[i] = 0;
+	if (FUSE)
+		for (int i = tid; i < ((NB + 32) << fbits); i += THREADS) sh2[i] = 0;
 	__syncthreads();
 
 	uint32_t cur_seg = 0xffffffffu;
@@ -85,6 +101,7 @@ histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t o
 			cur_seg = tile.seg;
 		}
 		const Seg s = segs[tile.seg];
+		if (s.skip & SEG_HIST_READY) continue;             // counted by the fused pass of the level above
 		const uint64_t *keys = s.buf ? c.keys[1] : c.keys[0];
 		const uint32_t end = s.begin + s.size;
 		const uint32_t lo = seg_tile_origin(s.begin) + tile.idx * TILE;
@@ -109,7 +126,7 @@ histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t o
 				validmask |= uint32_t(valid) << j;
 			}
 		}
-		hist_add_tile<ITEMS, NB>(sh, k, shift, origin, validmask);
+		hist_add_tile<ITEMS, NB, FUSE>(sh, k, shift, origin, validmask, sh2, fshift, fbits);
 	}
 	if (cur_seg != 0xffffffffu) {
 		__syncthreads();
@@ -117,6 +134,11 @@ histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t o
 			const uint32_t v = sh[b];
 			if (v) atomicAdd(&hist[size_t(cur_seg) * NB + b], v);
 		}
+		if (FUSE)
+			for (int i = tid; i < (NB << fbits); i += THREADS) {
+				const uint32_t v = sh2[i];
+				if (v) atomicAdd(&c.fused[i], v);
+			}
 	}
 }
 

@@ -50,6 +50,7 @@ __global__ void init_kernel(const Ctx c, const int bits0)
 	if (c.n > LOCAL_CAP) {
 		for (uint32_t i = gtid; i < nt; i += gsize) c.tiles[0][i] = Tile{0u, i};
 		for (uint32_t i = gtid; i < (1u << bits0); i += gsize) c.hist[0][i] = 0;
+		for (uint32_t i = gtid; i < (1u << FUSE_MAX_BITS); i += gsize) c.fused[i] = 0;
 	}
 }
 
@@ -64,9 +65,11 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v)
 }
 
 // Whole warp: make [begin, begin+size) in buffer `buf` a segment of level+1.
+// ready: the child's histogram (nbn counts) was computed by the fused pass, or NULL.
 __device__ __forceinline__ void emit_segment(const Ctx &c, Control *ctl, Seg *segs_out,
 					     Tile *tiles_out, uint32_t *hist_out, int level,
-					     uint32_t nbn, uint32_t begin, uint32_t size, uint32_t buf)
+					     uint32_t nbn, uint32_t begin, uint32_t size, uint32_t buf,
+					     const uint32_t *ready = nullptr)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t nt = seg_tile_count(begin, size);
@@ -75,13 +78,13 @@ __device__ __forceinline__ void emit_segment(const Ctx &c, Control *ctl, Seg *se
 		child = atomicAdd(&ctl->nsegs[level + 1], 1u);
 		tile_at = atomicAdd(&ctl->ntiles[level + 1], nt);
 		if (child >= c.max_segs) atomicOr(&ctl->error, 1u);
-		else segs_out[child] = Seg{begin, size, buf, 0u};
+		else segs_out[child] = Seg{begin, size, buf, ready ? SEG_HIST_READY : 0u};
 		if (tile_at + nt > c.max_tiles) atomicOr(&ctl->error, 2u);
 	}
 	child = __shfl_sync(0xffffffffu, child, 0);
 	tile_at = __shfl_sync(0xffffffffu, tile_at, 0);
 	if (child >= c.max_segs || tile_at + nt > c.max_tiles) return;
-	for (uint32_t j = lane; j < nbn; j += 32) hist_out[size_t(child) * nbn + j] = 0;
+	for (uint32_t j = lane; j < nbn; j += 32) hist_out[size_t(child) * nbn + j] = ready ? ready[j] : 0u;
 	for (uint32_t j = lane; j < nt; j += 32) tiles_out[tile_at + j] = Tile{child, j};
 }
 
@@ -104,9 +107,11 @@ __device__ __forceinline__ void emit_copy(const Ctx &c, Control *ctl, uint32_t b
 }
 
 // bits: digit width of this level; next_bits: of the next level (0 = this is the last);
-// shift: position of this level's digit in the key.
+// shift: position of this level's digit in the key; fused: c.fused holds the next level's digit
+// counts per bin of this level (level 0 only).
 __global__ void __launch_bounds__(PLAN_THREADS)
-plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, const int shift)
+plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, const int shift,
+	    const bool fused)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t warps_per_block = PLAN_THREADS / 32;
@@ -131,11 +136,18 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 		mx = __reduce_max_sync(0xffffffffu, mx);
 		if (mx == s.size) {
 			if (lane == 0) {
-				segs[sg].skip = 1;
+				segs[sg].skip = s.skip | SEG_SKIP;
 				atomicAdd(&ctl->degenerate, 1u);
 			}
-			if (!last)
-				emit_segment(c, ctl, segs_out, tiles_out, hist_out, level, NBN, s.begin, s.size, s.buf);
+			if (!last) {
+				// the one non-empty bin (for the fused histogram's row)
+				uint32_t full_bin = 0;
+				for (uint32_t b = lane; b < NB; b += 32)
+					if (h[b] == s.size) full_bin = b;
+				full_bin = __reduce_max_sync(0xffffffffu, full_bin);
+				emit_segment(c, ctl, segs_out, tiles_out, hist_out, level, NBN, s.begin, s.size, s.buf,
+					     fused ? c.fused + size_t(full_bin) * NBN : nullptr);
+			}
 			else if (s.buf == 1u)
 				emit_copy(c, ctl, s.begin, s.size);
 			continue;
@@ -162,7 +174,8 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 				large &= large - 1;
 				emit_segment(c, ctl, segs_out, tiles_out, hist_out, level, NBN,
 					     __shfl_sync(0xffffffffu, beg, src),
-					     __shfl_sync(0xffffffffu, cnt, src), dst_buf);
+					     __shfl_sync(0xffffffffu, cnt, src), dst_buf,
+					     fused ? c.fused + size_t(b0 + src) * NBN : nullptr);
 			}
 			// greedy merge of neighbouring small buckets into units (all lanes in step)
 			uint32_t present = __ballot_sync(0xffffffffu, cnt != 0);

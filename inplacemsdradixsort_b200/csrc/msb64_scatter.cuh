@@ -153,7 +153,7 @@ scatter_kernel(const Ctx c, const int level, const int shift, const uint32_t ori
 		slot->begin = s.begin;
 		slot->end = s.begin + s.size;
 		slot->lo = seg_tile_origin(s.begin) + tile.idx * TILE;
-		slot->flags = (s.buf ? TD_BUF : 0u) | (s.skip ? TD_SKIP : 0u);
+		slot->flags = (s.buf ? TD_BUF : 0u) | ((s.skip & SEG_SKIP) ? TD_SKIP : 0u);
 	};
 	// thread 0 only: a tile whose whole window lies inside the array is fetched by bulk
 	// copies (slots outside the segment receive the neighbours' data and are ignored)
