@@ -121,7 +121,7 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 		// 1. the unit's pairs are in (or on their way to) the registers
 		const Unit un = next;
 		const bool more = u + gridDim.x < nunits;
-		uint64_t *dst_keys = c.keys[0] + un.begin, *dst_rids = c.rids[0] + un.begin;
+		const uint32_t begin = un.begin;
 		const uint32_t size = un.size;
 		const uint32_t rows = (size + THREADS - 1) / THREADS;
 		// the bin table is free here (the previous unit is done with it)
@@ -171,8 +171,8 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 				for (int j = 0; j < ITEMS; ++j) {
 					const uint32_t i = j * THREADS + tid;
 					if (i < size) {
-						st_stream_u64(dst_keys + i, k[j]);
-						st_stream_u64(dst_rids + i, r[j]);
+						st_stream_u64(c.keys[0] + begin + i, k[j]);
+						st_stream_u64(c.rids[0] + begin + i, r[j]);
 					}
 				}
 			}
@@ -201,7 +201,9 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 
 		// branch-free inside a row (see tile_ranks in msb64_scatter.cuh): slots past the
 		// unit's end count into per-lane dummy bins behind the table
-		uint32_t rank[ITEMS];
+		uint32_t rk[ITEMS / 2];                 // arrival ranks, two 16-bit values per register
+#pragma unroll
+		for (int j = 0; j < ITEMS / 2; ++j) rk[j] = 0;
 		uint32_t *dummy = bins + LOCAL_NBINS + lane;
 #pragma unroll
 		for (int j = 0; j < ITEMS; ++j)
@@ -209,7 +211,7 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 				const uint32_t i = j * THREADS + tid;
 				const uint32_t d = uint32_t((k[j] - origin) >> shift) & dmask;
 				uint32_t *slot = i < size ? &bins[MSB64_BIN_SLOT(d)] : dummy;
-				rank[j] = atomicAdd(slot, 1u);
+				rk[j >> 1] |= atomicAdd(slot, 1u) << (16 * (j & 1));
 			}
 		__syncthreads();
 		// exclusive scan over bins in digit order; every bin becomes base | count << 16.
@@ -264,7 +266,7 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 				const uint32_t i = j * THREADS + tid;
 				if (i < size) {
 					const uint32_t d = uint32_t((k[j] - origin) >> shift) & dmask;
-					const uint32_t p = (bins[MSB64_BIN_SLOT(d)] & 0xffffu) + rank[j];
+					const uint32_t p = (bins[MSB64_BIN_SLOT(d)] & 0xffffu) + ((rk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
 					skeys[p] = k[j];
 					srids[p] = r[j];
 				}
@@ -303,6 +305,18 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 			const uint32_t pk = list[q];
 			uint64_t *bk = skeys + (pk & 0xffffu), *br = srids + (pk & 0xffffu);
 			const uint32_t cnt = pk >> 16;
+			if (cnt == 2) {
+				// the common case: rids are touched only when the two keys are out of order
+				const uint64_t a0 = bk[0], a1 = bk[1];
+				if (a0 > a1) {
+					const uint64_t b0 = br[0], b1 = br[1];
+					bk[0] = a1;
+					bk[1] = a0;
+					br[0] = b1;
+					br[1] = b0;
+				}
+				continue;
+			}
 			if (cnt <= 4) {
 				uint64_t a0 = bk[0], a1 = bk[1], b0 = br[0], b1 = br[1];
 				uint64_t a2 = ~0ull, a3 = ~0ull, b2 = 0, b3 = 0;
@@ -365,8 +379,8 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 
 		// 4. home (the next unit's first barrier orders these reads before its stores)
 		for (uint32_t i = tid; i < size; i += THREADS) {
-			st_stream_u64(dst_keys + i, skeys[i]);
-			st_stream_u64(dst_rids + i, srids[i]);
+			st_stream_u64(c.keys[0] + begin + i, skeys[i]);
+			st_stream_u64(c.rids[0] + begin + i, srids[i]);
 		}
 #undef MSB64_BIN_SLOT
 	}
