@@ -382,7 +382,8 @@ def main_b200(args):
             }
             kernels["scatter"] = {"GB/s": ach, "frac": ach / peak, "ms": us / 1e3}
             hus = sum(levels[l]["histogram"] for l in range(len(levels)) if moved[l])
-            hb = sum(8 * p for p, _ in active)
+            # keys the histogram passes really read (level 1 is counted inside level 0's pass)
+            hb = 8 * stats["hist_keys"] if stats.get("hist_keys") else sum(8 * p for p, _ in active)
             if hus:
                 kernels["histogram"] = {"GB/s": hb / (hus * 1e-6) / 1e9,
                                         "frac": hb / (hus * 1e-6) / 1e9 / peak, "ms": hus / 1e3}

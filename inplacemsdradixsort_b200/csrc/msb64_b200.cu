@@ -79,8 +79,11 @@ std::vector<int> make_schedule(uint64_t n, int width = 64)
 	// falls with the run length TILE / 2^bits (tools/permcopy.cu: 6.3 TB/s at 256-byte
 	// runs, 3.5 TB/s at 64-byte runs), so the `need` bits are spread over the fewest
 	// passes of at most 8 bits, as evenly as possible, widest first.
+	// log2(n) rounded to the nearest integer (a receive count just above a power of two
+	// must not buy a whole extra bit: buckets of 2100 pairs are as good as 2048)
 	int log_n = 0;
-	while (log_n < 63 && (1ull << log_n) < n) ++log_n;
+	while (log_n < 63 && (2ull << log_n) <= n) ++log_n;                       // floor(log2 n)
+	if (log_n < 63 && double(n) > 1.41421356 * double(1ull << log_n)) ++log_n;
 	int need = log_n > 11 ? log_n - 11 : 0;
 	if (need > width) need = width;
 	std::vector<int> s;
@@ -687,6 +690,7 @@ int msb64_b200_last_stats(uint64_t *out, int cap)
 	if (k < cap) out[k++] = h.degenerate;
 	if (k < cap) out[k++] = h.local_pairs;
 	for (int l = 0; l < MAX_LEVELS && k < cap; ++l) out[k++] = h.moved[l];
+	if (k < cap) out[k++] = h.hist_keys;
 	return k;
 }
 

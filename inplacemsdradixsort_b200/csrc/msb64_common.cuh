@@ -79,6 +79,8 @@ struct Control {
 	uint32_t degenerate;     // segments whose scatter was skipped (statistics)
 	uint32_t moved[MAX_LEVELS];   // pairs the scatter of each level moves (statistics)
 	uint32_t local_pairs;    // pairs finished by the local sort (statistics)
+	uint32_t nready[MAX_LEVELS + 1];  // segments of each level whose histogram the level above computed
+	unsigned long long hist_keys;     // keys read by histogram passes (statistics)
 };
 
 // Everything a kernel needs, passed by value.

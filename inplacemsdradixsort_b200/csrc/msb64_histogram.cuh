@@ -74,6 +74,7 @@ histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t o
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ntiles = c.ctl->ntiles[level];
+	if (!FUSE && c.ctl->nready[level] == c.ctl->nsegs[level]) return;    // every histogram came from the fused pass
 	const Seg *segs = (level & 1) ? c.segs[1] : c.segs[0];
 	const Tile *tiles = (level & 1) ? c.tiles[1] : c.tiles[0];
 	uint32_t *hist = (level & 1) ? c.hist[1] : c.hist[0];

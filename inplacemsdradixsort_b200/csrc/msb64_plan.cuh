@@ -31,12 +31,14 @@ __global__ void init_kernel(const Ctx c, const int bits0)
 		for (int l = 0; l <= MAX_LEVELS; ++l) {
 			ctl->nsegs[l] = 0;
 			ctl->ntiles[l] = 0;
+			ctl->nready[l] = 0;
 		}
 		ctl->nunits = 0;
 		ctl->ncopies = 0;
 		ctl->error = 0;
 		ctl->degenerate = 0;
 		ctl->local_pairs = c.n <= LOCAL_CAP ? c.n : 0;
+		ctl->hist_keys = c.n > LOCAL_CAP ? c.n : 0;
 		for (int l = 0; l < MAX_LEVELS; ++l) ctl->moved[l] = 0;
 		if (c.n > LOCAL_CAP) {
 			ctl->nsegs[0] = 1;
@@ -80,6 +82,8 @@ __device__ __forceinline__ void emit_segment(const Ctx &c, Control *ctl, Seg *se
 		if (child >= c.max_segs) atomicOr(&ctl->error, 1u);
 		else segs_out[child] = Seg{begin, size, buf, ready ? SEG_HIST_READY : 0u};
 		if (tile_at + nt > c.max_tiles) atomicOr(&ctl->error, 2u);
+		if (ready) atomicAdd(&ctl->nready[level + 1], 1u);
+		else atomicAdd(&ctl->hist_keys, (unsigned long long) size);
 	}
 	child = __shfl_sync(0xffffffffu, child, 0);
 	tile_at = __shfl_sync(0xffffffffu, tile_at, 0);

@@ -380,4 +380,5 @@ def last_stats() -> dict:
     if k < 53:
         return {}
     return {"segments": v[0:16], "tiles": v[16:32], "units": v[32], "copy_tiles": v[33],
-            "error": v[34], "degenerate": v[35], "local_pairs": v[36], "moved": v[37:53]}
+            "error": v[34], "degenerate": v[35], "local_pairs": v[36], "moved": v[37:53],
+            "hist_keys": v[53] if k > 53 else None}

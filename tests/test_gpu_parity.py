@@ -169,3 +169,26 @@ def test_sort_with_known_key_range(gpu, lo, hi, n):
     order = np.lexsort((rids, keys))
     assert np.array_equal(gk, keys[order])
     assert np.array_equal(gr[np.lexsort((gr, gk))], rids[order])
+
+
+FULL = [("uniform", 0, 0), ("few_distinct_16", 2, 16), ("heavy_duplicates_1e6", 2, 1_000_000),
+        ("low_24_bits", 1, 0xFFFFFF), ("presorted", 3, 1), ("reverse_sorted", 4, 1)]
+
+
+@pytest.mark.parametrize("name,kind,param", FULL, ids=[f[0] for f in FULL])
+def test_full_size_properties(gpu, name, kind, param):
+    """BASELINE.json's full size (2^30 pairs, configs[1]-[3]) through size-independent
+    properties: ascending, wrapping key sum and order-independent (key, rid) digest unchanged
+    (the reference's check(), msb_64.c:2432-2505), and idempotence (sorting the sorted
+    output changes nothing but possibly the order of rids among equal keys)."""
+    n = 1 << 30
+    with gpu.DeviceArray(n) as dk, gpu.DeviceArray(n) as dr:
+        gpu.fill(dk, dr, kind=kind, seed=2026, param=param)
+        bad0, sum0, dig0 = dk.check(dr)
+        gpu.sort_device(dk.ptr, dr.ptr, n)
+        bad1, sum1, dig1 = dk.check(dr)
+        assert bad1 == 0, f"{bad1} descents"
+        assert (sum1, dig1) == (sum0, dig0), "key checksum / (key, rid) multiset changed"
+        assert gpu.last_stats()["error"] == 0
+        gpu.sort_device(dk.ptr, dr.ptr, n)
+        assert dk.check(dr) == (0, sum0, dig0), "not idempotent"
