@@ -320,8 +320,9 @@ def main_b200(args):
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {
-            "workload": f"uniform 64-bit key + 64-bit rid pairs, {n} per GPU "
-                        f"(BASELINE.json configs[1]{'' if world == 1 else ', sharded x' + str(world)})",
+            "workload": f"uniform 64-bit key + 64-bit rid pairs, {n} per GPU " + (
+                "(BASELINE.json configs[4]: 2^34 pairs over 8 GPUs)" if n * world == 1 << 34 and world == 8 else
+                f"(BASELINE.json configs[1]{'' if world == 1 else ', one such shard per GPU x' + str(world)})"),
             "pairs_per_gpu": n, "total_pairs": n * world,
             "l2": "inputs (16 B x pairs per GPU) far exceed the 126 MB L2; every step re-reads "
                   "a fresh unsorted copy",
