@@ -24,6 +24,7 @@
 #include "msb64_common.cuh"
 #include "msb64_histogram.cuh"
 #include "msb64_local_sort.cuh"
+#include "msb64_local_packed.cuh"
 #include "msb64_plan.cuh"
 #include "msb64_scatter.cuh"
 #include "msb64_route.cuh"
@@ -144,7 +145,7 @@ struct Device {
 	int hist_blocks[MAX_BITS + 1] = {0};      // resident blocks per SM, by digit width
 	int fused_blocks[MAX_BITS + 1] = {0};     // same for the fused (two-level) histogram
 	int scatter_blocks[MAX_BITS + 1] = {0};
-	int local_blocks = 0;
+	int local_blocks = 0, packed_blocks = 0;
 	// cached allocations (grow-only)
 	void *ws = nullptr;
 	size_t ws_bytes = 0;
@@ -211,6 +212,11 @@ int device_init()
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_dev.local_blocks, local_sort_kernel,
 							       LOCAL_THREADS, LOCAL_SMEM));
 	if (g_dev.local_blocks < 1) return fail(MSB64_ERR_CUDA, "local sort does not fit on an SM%s");
+	CUDA_TRY(cudaFuncSetAttribute(local_sort_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				      int(PACKED_SMEM)));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_dev.packed_blocks, local_sort_packed_kernel,
+							       LOCAL_THREADS, PACKED_SMEM));
+	if (g_dev.packed_blocks < 1) return fail(MSB64_ERR_CUDA, "packed local sort does not fit on an SM%s");
 	CUDA_TRY(cudaStreamCreateWithFlags(&g_dev.stream, cudaStreamNonBlocking));
 	g_dev.ready = true;
 	return MSB64_OK;
@@ -363,8 +369,13 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	}
 	cudaEvent_t *tail = ev ? ev + 1 + 4 * levels : nullptr;
 	if (tail) cudaEventRecord(tail[0], st);
+	// units whose keys leave room for a slot number in one word take the packed path, the rest
+	// (small arrays, very deep levels never) the general one; an empty list costs a launch
+	local_sort_packed_kernel<<<g_dev.sms * g_dev.packed_blocks, LOCAL_THREADS, PACKED_SMEM, st>>>(
+		c, uint32_t(rp.shift0), rp.origin0 << rp.shift0);
 	local_sort_kernel<<<g_dev.sms * g_dev.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(
 		c, uint32_t(rp.shift0), rp.origin0 << rp.shift0);
+	g_launches += 1;
 	if (tail) cudaEventRecord(tail[1], st);
 	copy_kernel<<<g_dev.sms * 8, 256, 0, st>>>(c);
 	if (tail) cudaEventRecord(tail[2], st);
@@ -684,7 +695,7 @@ int msb64_b200_last_stats(uint64_t *out, int cap)
 	int k = 0;
 	for (int l = 0; l < MAX_LEVELS && k < cap; ++l) out[k++] = h.nsegs[l];
 	for (int l = 0; l < MAX_LEVELS && k < cap; ++l) out[k++] = h.ntiles[l];
-	if (k < cap) out[k++] = h.nunits;
+	if (k < cap) out[k++] = h.nunits + h.nslow;
 	if (k < cap) out[k++] = h.ncopies;
 	if (k < cap) out[k++] = h.error;
 	if (k < cap) out[k++] = h.degenerate;

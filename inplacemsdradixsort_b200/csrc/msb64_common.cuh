@@ -27,7 +27,10 @@ constexpr int MAX_BITS = 11;            // widest digit a level may use
 #define MSB64_LOCAL_CAP 4096
 #endif
 constexpr uint32_t LOCAL_CAP = MSB64_LOCAL_CAP;   // pairs the local sort holds in shared memory
-constexpr uint32_t TILE = 4096;         // element slots per histogram/scatter tile
+#ifndef MSB64_TILE
+#define MSB64_TILE 4096
+#endif
+constexpr uint32_t TILE = MSB64_TILE;   // element slots per histogram/scatter tile
 constexpr uint32_t COPY_TILE = 8192;    // pairs per copy tile
 constexpr int FUSE_MAX_BITS = 13;       // level 0 + level 1 digit bits the fused histogram pass handles (32 KiB of counters)
 
@@ -52,17 +55,19 @@ struct Unit {
 	uint32_t origin;  // unit_origin(): digit position and first digit of the run of buckets
 };
 
-// A unit is a run of buckets with consecutive digits first, first+1, ... at bit position
-// `shift`: its keys lie in a contiguous key range that starts at prefix | first << shift.
-// The local sort subtracts that origin so that the keys of a unit made of several
-// buckets spread evenly over its counting bins.
-__host__ __device__ inline uint32_t unit_origin(int shift, uint32_t first_digit)
+// A unit is a run of buckets with consecutive digits first, first+1, ... of a `bits`-wide
+// digit at bit position `shift`: its keys lie in a contiguous key range that starts at
+// prefix | first << shift and agree on every bit above shift + bits.  The local sort
+// subtracts that origin so that the keys of a unit made of several buckets spread evenly
+// over its counting bins.  origin word: shift [0,6) | bits [6,10) | first digit [10,22);
+// bits = 0: nothing is known about the unit's keys (a whole small array).
+__host__ __device__ inline uint32_t unit_origin(int shift, uint32_t first_digit, int bits)
 {
-	return uint32_t(shift) | (first_digit << 8);
+	return uint32_t(shift) | (uint32_t(bits) << 6) | (first_digit << 10);
 }
 __host__ __device__ inline uint64_t unit_origin_key(uint32_t origin)
 {
-	return uint64_t(origin >> 8) << (origin & 63u);
+	return uint64_t(origin >> 10) << (origin & 63u);
 }
 
 struct CopyTile {
@@ -73,7 +78,8 @@ struct CopyTile {
 struct Control {
 	uint32_t nsegs[MAX_LEVELS + 1];
 	uint32_t ntiles[MAX_LEVELS + 1];
-	uint32_t nunits;
+	uint32_t nunits;         // units of the packed local sort, filed from the front of `units`
+	uint32_t nslow;          // units of the general local sort, filed from the back
 	uint32_t ncopies;
 	uint32_t error;          // bit 0: Seg list overflow, 1: Tile, 2: Unit, 3: CopyTile
 	uint32_t degenerate;     // segments whose scatter was skipped (statistics)

@@ -91,7 +91,8 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 	__shared__ uint32_t s_nbig;
 
 	const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-	const uint32_t nunits = min(c.ctl->nunits, c.max_units);
+	const uint32_t nunits = min(c.ctl->nslow, c.max_units);          // this kernel's units sit at the back
+	const Unit *units = c.units + c.max_units - 1;                   // unit i is units[-i]
 
 	// The loop is software-pipelined: the pairs of the NEXT unit are requested from HBM as
 	// soon as the current unit's pairs have left the registers for shared memory (after step
@@ -113,7 +114,7 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 	};
 	Unit next = Unit{0u, 1u, 0u, 0u};
 	if (blockIdx.x < nunits) {
-		next = c.units[blockIdx.x];
+		next = *(units - blockIdx.x);
 		load_unit(next);
 	}
 
@@ -178,7 +179,7 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 			}
 			__syncthreads();
 			if (more) {
-				next = c.units[u + gridDim.x];
+				next = *(units - (u + gridDim.x));
 				load_unit(next);
 			}
 			continue;
@@ -294,7 +295,7 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 		}
 		// the registers are free: request the next unit's pairs now
 		if (more) {
-			next = c.units[u + gridDim.x];
+			next = *(units - (u + gridDim.x));
 			load_unit(next);
 		}
 		// 3b. one thread per short colliding bin.  Up to four pairs (nearly all of them):

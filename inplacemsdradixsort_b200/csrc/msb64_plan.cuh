@@ -15,6 +15,7 @@
 //     copy tiles.
 #pragma once
 #include "msb64_common.cuh"
+#include "msb64_local_packed.cuh"   // unit_packable
 
 namespace msb64 {
 
@@ -34,6 +35,7 @@ __global__ void init_kernel(const Ctx c, const int bits0)
 			ctl->nready[l] = 0;
 		}
 		ctl->nunits = 0;
+		ctl->nslow = 0;
 		ctl->ncopies = 0;
 		ctl->error = 0;
 		ctl->degenerate = 0;
@@ -45,8 +47,8 @@ __global__ void init_kernel(const Ctx c, const int bits0)
 			ctl->ntiles[0] = nt;
 			c.segs[0][0] = Seg{0u, c.n, 0u, 0u};
 		} else if (c.n > 0) {
-			ctl->nunits = 1;
-			c.units[0] = Unit{0u, c.n, 0u, 0u};
+			ctl->nslow = 1;                                  // nothing known about the keys: general path
+			c.units[c.max_units - 1] = Unit{0u, c.n, 0u, 0u};
 		}
 	}
 	if (c.n > LOCAL_CAP) {
@@ -90,6 +92,22 @@ __device__ __forceinline__ void emit_segment(const Ctx &c, Control *ctl, Seg *se
 	if (child >= c.max_segs || tile_at + nt > c.max_tiles) return;
 	for (uint32_t j = lane; j < nbn; j += 32) hist_out[size_t(child) * nbn + j] = ready ? ready[j] : 0u;
 	for (uint32_t j = lane; j < nt; j += 32) tiles_out[tile_at + j] = Tile{child, j};
+}
+
+// One lane: file a unit for the local sort -- packed path from the front of the array,
+// general path from the back.
+__device__ __forceinline__ void emit_unit(const Ctx &c, Control *ctl, uint32_t begin, uint32_t size,
+					  uint32_t buf, uint32_t origin)
+{
+	const bool fast = unit_packable(origin);
+	const uint32_t at = atomicAdd(fast ? &ctl->nunits : &ctl->nslow, 1u);
+	// the two lists grow towards each other
+	const uint32_t other = *reinterpret_cast<volatile uint32_t *>(fast ? &ctl->nslow : &ctl->nunits);
+	if (at + other >= c.max_units) {
+		atomicOr(&ctl->error, 4u);
+		return;
+	}
+	c.units[fast ? at : c.max_units - 1 - at] = Unit{begin, size, buf, origin};
 }
 
 // Whole warp: final data of [begin, begin+size) sits in B, schedule its copy to A.
@@ -189,11 +207,8 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 				const uint32_t cb = __shfl_sync(0xffffffffu, cnt, src);
 				const uint32_t bb = __shfl_sync(0xffffffffu, beg, src);
 				if (cb > LOCAL_CAP || run_size + cb > LOCAL_CAP) {
-					if (run_size && lane == 0) {
-						const uint32_t u = atomicAdd(&ctl->nunits, 1u);
-						if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, unit_origin(shift, run_dig)};
-						else atomicOr(&ctl->error, 4u);
-					}
+					if (run_size && lane == 0)
+						emit_unit(c, ctl, run_beg, run_size, dst_buf, unit_origin(shift, run_dig, bits));
 					local_pairs += run_size;
 					run_size = 0;
 					if (cb > LOCAL_CAP) continue;
@@ -206,11 +221,8 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 			}
 		}
 		if (!last) {
-			if (run_size && lane == 0) {
-				const uint32_t u = atomicAdd(&ctl->nunits, 1u);
-				if (u < c.max_units) c.units[u] = Unit{run_beg, run_size, dst_buf, unit_origin(shift, run_dig)};
-				else atomicOr(&ctl->error, 4u);
-			}
+			if (run_size && lane == 0)
+				emit_unit(c, ctl, run_beg, run_size, dst_buf, unit_origin(shift, run_dig, bits));
 			local_pairs += run_size;
 			if (local_pairs && lane == 0) atomicAdd(&ctl->local_pairs, local_pairs);
 		} else if (dst_buf == 1u) {
