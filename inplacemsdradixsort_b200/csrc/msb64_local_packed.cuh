@@ -100,6 +100,7 @@ local_sort_packed_kernel(const Ctx c, const uint32_t base_shift, const uint64_t 
 	for (uint32_t u = blockIdx.x; u < nunits; u += gridDim.x) {
 		const Unit un = next;
 		const bool more = u + gridDim.x < nunits;
+		if (more) next = c.units[u + gridDim.x];                 // descriptor now, keys when the registers are free
 		const uint32_t begin = un.begin, size = un.size;
 		const uint32_t rows = (size + THREADS - 1) / THREADS;
 		// the rids' 16-byte aligned window [begin - a, ...) and how much of it a bulk copy may
@@ -174,10 +175,7 @@ local_sort_packed_kernel(const Ctx c, const uint32_t base_shift, const uint64_t 
 					}
 				}
 			}
-			if (more) {
-				next = c.units[u + gridDim.x];
-				load_keys(next);
-			}
+			if (more) load_keys(next);
 			continue;
 		}
 
@@ -283,10 +281,7 @@ local_sort_packed_kernel(const Ctx c, const uint32_t base_shift, const uint64_t 
 			if (tid < nbig) big[tid] = bins[big[tid]];
 		}
 		// the registers are free: request the next unit's keys now
-		if (more) {
-			next = c.units[u + gridDim.x];
-			load_keys(next);
-		}
+		if (more) load_keys(next);
 		// 3b. one thread per short colliding bin: words only, the rids stay where they are
 		for (uint32_t q = tid; q < nlist; q += THREADS) {
 			const uint32_t e = list[q];

@@ -101,9 +101,8 @@ __device__ __forceinline__ void emit_unit(const Ctx &c, Control *ctl, uint32_t b
 {
 	const bool fast = unit_packable(origin);
 	const uint32_t at = atomicAdd(fast ? &ctl->nunits : &ctl->nslow, 1u);
-	// the two lists grow towards each other
-	const uint32_t other = *reinterpret_cast<volatile uint32_t *>(fast ? &ctl->nslow : &ctl->nunits);
-	if (at + other >= c.max_units) {
+	// the two lists grow towards each other; max_units bounds their sum (copy_kernel checks it)
+	if (at >= c.max_units) {
 		atomicOr(&ctl->error, 4u);
 		return;
 	}
@@ -235,6 +234,8 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 __global__ void __launch_bounds__(256)
 copy_kernel(const Ctx c)
 {
+	if (blockIdx.x == 0 && threadIdx.x == 0 && c.ctl->nunits + c.ctl->nslow > c.max_units)
+		atomicOr(&c.ctl->error, 4u);                  // the two unit lists ran into each other
 	const uint32_t ncopies = min(c.ctl->ncopies, c.max_copies);
 	for (uint32_t t = blockIdx.x; t < ncopies; t += gridDim.x) {
 		const CopyTile ct = c.copies[t];
