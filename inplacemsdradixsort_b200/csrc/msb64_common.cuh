@@ -112,28 +112,6 @@ __host__ __device__ inline uint32_t seg_tile_count(uint32_t begin, uint32_t size
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ uint32_t lanemask_lt()
-{
-	uint32_t m;
-	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-	return m;
-}
-
-// Lanes of the warp whose `digit` equals mine (warp-level multisplit by ballots:
-// one vote per digit bit; no shared-memory atomics on the hot path).
-template <int BITS>
-__device__ __forceinline__ uint32_t match_digit(uint32_t digit)
-{
-	uint32_t peers = 0xffffffffu;
-#pragma unroll
-	for (int b = 0; b < BITS; ++b) {
-		const bool bit = (digit >> b) & 1u;
-		const uint32_t votes = __ballot_sync(0xffffffffu, bit);
-		peers &= bit ? votes : ~votes;
-	}
-	return peers;
-}
-
 // Streaming 16-byte / 8-byte global accesses: the sort touches every byte once per
 // pass, so nothing is worth keeping in L1.
 __device__ __forceinline__ ulonglong2 ld_stream_u64x2(const uint64_t *p)
