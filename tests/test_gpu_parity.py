@@ -192,3 +192,43 @@ def test_full_size_properties(gpu, name, kind, param):
         assert gpu.last_stats()["error"] == 0
         gpu.sort_device(dk.ptr, dr.ptr, n)
         assert dk.check(dr) == (0, sum0, dig0), "not idempotent"
+
+
+def test_random_sizes_and_kinds(gpu):
+    """Many ragged sizes x input families (unit tails, odd offsets, arrays ending inside a
+    tile): keys must equal the sorted keys and the (key, rid) multiset must be unchanged.
+    The expected order comes from numpy here (the oracle's order is pinned to it elsewhere)."""
+    rng = np.random.default_rng(20261018)
+    for case in range(120):
+        kind = KINDS[int(rng.integers(0, len(KINDS)))]
+        n = int(rng.choice([rng.integers(1, 300), rng.integers(300, 9000), rng.integers(9000, 400_000)]))
+        keys = make(kind, n, seed=1000 + case)
+        rids = rng.integers(0, 1 << 64, size=n, dtype=np.uint64)
+        gk, gr = keys.copy(), rids.copy()
+        gpu.sort_pairs(gk, gr)
+        order = np.lexsort((rids, keys))
+        assert np.array_equal(gk, keys[order]), f"case {case}: {kind} n={n}: keys"
+        assert np.array_equal(gr[np.lexsort((gr, gk))], rids[order]), f"case {case}: {kind} n={n}: rids"
+
+
+def test_device_sort_at_odd_offsets(gpu):
+    """Device arrays that start and end at odd element offsets inside a larger allocation
+    (16-byte alignment of the bulk copies must not leak into the interface: the C ABI asks
+    for 16-byte aligned arrays, so the offset is even, but lengths are arbitrary)."""
+    n_total = 1_200_007
+    base = make("uniform", n_total, seed=77)
+    for off, n in [(0, 1_200_007), (2, 1_200_005), (4098, 777_777), (65538, 4097), (8, 2_001)]:
+        keys = base[off: off + n].copy()
+        rids = np.arange(n, dtype=np.uint64)
+        with gpu.DeviceArray(n_total) as dk, gpu.DeviceArray(n_total) as dr:
+            dk.upload(base)
+            full_r = np.zeros(n_total, dtype=np.uint64)
+            full_r[off: off + n] = rids
+            dr.upload(full_r)
+            gpu.sort_device(dk.ptr + 8 * off, dr.ptr + 8 * off, n)
+            out_k, out_r = dk.download(), dr.download()
+        assert np.array_equal(out_k[:off], base[:off]) and np.array_equal(out_k[off + n:], base[off + n:]), \
+            "the sort touched elements outside its arrays"
+        assert np.array_equal(out_k[off: off + n], np.sort(keys))
+        got_r = out_r[off: off + n]
+        assert np.array_equal(keys[got_r.astype(np.int64)], out_k[off: off + n]), "rid does not point at its key"
