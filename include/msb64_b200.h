@@ -175,17 +175,22 @@ int msb64_b200_check(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
  * 497-699, 1546-1606); the collectives between them are the caller's
  * (inplacemsdradixsort_b200/distributed.py uses NCCL through torch.distributed).
  *
- * msb64_b200_digit_histogram: d_hist[0 .. 2^bits) = number of keys whose bits
- *   [shift, shift+bits) equal the index (bits <= 12).  d_hist is zeroed first.
+ * Digits of these steps: digit(key) = ((key >> shift) - origin) & (2^bits - 1), bits <= 13.
+ * With origin = 0 that is a plain bit field; a caller that knows the smallest key (below)
+ * passes origin = smallest >> shift and a shift chosen for the keys' real span, so that
+ * keys sharing a long prefix (only low bits significant) still spread over the bins.
+ *
+ * msb64_b200_digit_histogram: d_hist[0 .. 2^bits) = number of keys per digit (zeroed
+ *   first).  d_minmax: NULL, or two words that receive the smallest and the largest key.
  * msb64_b200_route: groups the n pairs by destination = d_bin_to_dest[digit] (one byte
  *   per bin, ndest <= 64 destinations) into d_out_keys / d_out_rids; d_cursors[dest]
  *   must hold the first output slot of each destination (exclusive prefix of the
  *   per-destination counts) and is advanced by the kernel.  Order inside a
  *   destination is unspecified. */
 int msb64_b200_digit_histogram(const uint64_t *d_keys, uint64_t n, int shift, int bits,
-			       uint64_t *d_hist, void *stream);
+			       uint64_t origin, uint64_t *d_hist, uint64_t *d_minmax, void *stream);
 int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
-		     int shift, int bits, const uint8_t *d_bin_to_dest, int ndest,
+		     int shift, int bits, uint64_t origin, const uint8_t *d_bin_to_dest, int ndest,
 		     uint32_t *d_cursors, uint64_t *d_out_keys, uint64_t *d_out_rids,
 		     void *stream);
 
@@ -204,7 +209,7 @@ int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
  * a peer's allocation and enables peer access; returns NULL on failure. */
 #define MSB64_IPC_HANDLE_BYTES 64
 int msb64_b200_route_peer(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
-			  int shift, int bits, const uint8_t *d_bin_to_dest, int ndest,
+			  int shift, int bits, uint64_t origin, const uint8_t *d_bin_to_dest, int ndest,
 			  uint32_t *d_cursors, uint64_t *const *out_keys,
 			  uint64_t *const *out_rids, void *stream);
 int msb64_b200_ipc_export(void *d_ptr, void *handle64);

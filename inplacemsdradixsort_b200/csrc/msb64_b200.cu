@@ -714,20 +714,25 @@ int msb64_b200_last_level_times(uint64_t *out, int cap)
 	return k;
 }
 
-int msb64_b200_digit_histogram(const uint64_t *d_keys, uint64_t n, int shift, int bits,
-				uint64_t *d_hist, void *stream)
+int msb64_b200_digit_histogram(const uint64_t *d_keys, uint64_t n, int shift, int bits, uint64_t origin,
+				uint64_t *d_hist, uint64_t *d_minmax, void *stream)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
 	int rc = device_init();
 	if (rc) return rc;
-	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift + bits > 64 || !d_hist)
+	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift >= 64 || !d_hist)
 		return fail(MSB64_ERR_ARG, "digit_histogram: bad shift/bits%s");
 	if (n > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) << bits, st));
+	if (d_minmax) {
+		CUDA_TRY(cudaMemsetAsync(d_minmax, 0xff, sizeof(uint64_t), st));
+		CUDA_TRY(cudaMemsetAsync(d_minmax + 1, 0, sizeof(uint64_t), st));
+	}
 	if (n) {
 		digit_histogram_kernel<<<g_dev.sms * 8, 256, sizeof(uint32_t) << bits, st>>>(
-			d_keys, n, shift, bits, reinterpret_cast<unsigned long long *>(d_hist));
+			d_keys, n, shift, bits, uint32_t(origin), reinterpret_cast<unsigned long long *>(d_hist),
+			reinterpret_cast<unsigned long long *>(d_minmax));
 		g_launches += 1;
 	}
 	CUDA_TRY(cudaGetLastError());
@@ -735,12 +740,12 @@ int msb64_b200_digit_histogram(const uint64_t *d_keys, uint64_t n, int shift, in
 }
 
 static int route_common(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, int shift, int bits,
-			const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors, const RouteDst &dst,
+			uint64_t origin, const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors, const RouteDst &dst,
 			void *stream)
 {
 	int rc = device_init();
 	if (rc) return rc;
-	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift + bits > 64 || ndest < 1 ||
+	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift >= 64 || ndest < 1 ||
 	    ndest > ROUTE_MAX_DEST || !d_bin_to_dest || !d_cursors)
 		return fail(MSB64_ERR_ARG, "route: bad shift/bits/ndest%s");
 	if (n > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
@@ -756,17 +761,17 @@ static int route_common(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if (ndest <= 16)
 		route_kernel<16><<<g_dev.sms * 3, ROUTE_THREADS, RouteCfg<16>::SMEM, st>>>(
-			d_keys, d_rids, uint32_t(n), shift, bits, d_bin_to_dest, ndest, d_cursors, dst);
+			d_keys, d_rids, uint32_t(n), shift, bits, uint32_t(origin), d_bin_to_dest, ndest, d_cursors, dst);
 	else
 		route_kernel<ROUTE_MAX_DEST><<<g_dev.sms * 2, ROUTE_THREADS, RouteCfg<ROUTE_MAX_DEST>::SMEM, st>>>(
-			d_keys, d_rids, uint32_t(n), shift, bits, d_bin_to_dest, ndest, d_cursors, dst);
+			d_keys, d_rids, uint32_t(n), shift, bits, uint32_t(origin), d_bin_to_dest, ndest, d_cursors, dst);
 	g_launches += 1;
 	CUDA_TRY(cudaGetLastError());
 	return MSB64_OK;
 }
 
 int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, int shift, int bits,
-		     const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors,
+		     uint64_t origin, const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors,
 		     uint64_t *d_out_keys, uint64_t *d_out_rids, void *stream)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
@@ -775,11 +780,11 @@ int msb64_b200_route(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
 		dst.keys[i] = d_out_keys;
 		dst.rids[i] = d_out_rids;
 	}
-	return route_common(d_keys, d_rids, n, shift, bits, d_bin_to_dest, ndest, d_cursors, dst, stream);
+	return route_common(d_keys, d_rids, n, shift, bits, origin, d_bin_to_dest, ndest, d_cursors, dst, stream);
 }
 
 int msb64_b200_route_peer(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, int shift, int bits,
-			  const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors,
+			  uint64_t origin, const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors,
 			  uint64_t *const *out_keys, uint64_t *const *out_rids, void *stream)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
@@ -790,7 +795,7 @@ int msb64_b200_route_peer(const uint64_t *d_keys, const uint64_t *d_rids, uint64
 		dst.keys[i] = out_keys[i < ndest ? i : 0];
 		dst.rids[i] = out_rids[i < ndest ? i : 0];
 	}
-	return route_common(d_keys, d_rids, n, shift, bits, d_bin_to_dest, ndest, d_cursors, dst, stream);
+	return route_common(d_keys, d_rids, n, shift, bits, origin, d_bin_to_dest, ndest, d_cursors, dst, stream);
 }
 
 int msb64_b200_ipc_export(void *d_ptr, void *handle64)

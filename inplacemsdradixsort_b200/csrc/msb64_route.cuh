@@ -25,11 +25,13 @@ namespace msb64 {
 constexpr int ROUTE_THREADS = 256;
 constexpr int ROUTE_ITEMS = TILE / ROUTE_THREADS;
 constexpr int ROUTE_MAX_DEST = 64;
-constexpr int ROUTE_MAX_BITS = 12;
+constexpr int ROUTE_MAX_BITS = 13;
 
+// digit = ((key >> shift) - origin) & (2^bits - 1); minmax (optional): [0] = smallest, [1] =
+// largest key seen (initialised by the host to ~0 and 0).
 __global__ void __launch_bounds__(256)
-digit_histogram_kernel(const uint64_t *keys, uint64_t n, int shift, int bits,
-		       unsigned long long *hist)
+digit_histogram_kernel(const uint64_t *keys, uint64_t n, int shift, int bits, uint32_t origin,
+		       unsigned long long *hist, unsigned long long *minmax)
 {
 	extern __shared__ uint32_t sh[];
 	const uint32_t nb = 1u << bits;
@@ -39,11 +41,28 @@ digit_histogram_kernel(const uint64_t *keys, uint64_t n, int shift, int bits,
 	for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
 	__syncthreads();
 	// 32-bit block counters: a block never sees more than 2^32 keys (n <= MSB64_MAX_PAIRS)
-	for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
-		atomicAdd(&sh[uint32_t(ld_stream_u64(keys + i) >> shift) & (nb - 1)], 1u);
+	unsigned long long kmin = ~0ull, kmax = 0;
+	for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		const uint64_t k = ld_stream_u64(keys + i);
+		kmin = k < kmin ? k : kmin;
+		kmax = k > kmax ? k : kmax;
+		atomicAdd(&sh[(uint32_t(k >> shift) - origin) & (nb - 1)], 1u);
+	}
 	__syncthreads();
 	for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x)
 		if (sh[i]) atomicAdd(&hist[i], (unsigned long long) sh[i]);
+	if (minmax) {
+		for (int d = 16; d; d >>= 1) {
+			const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, d);
+			const unsigned long long b = __shfl_xor_sync(0xffffffffu, kmax, d);
+			kmin = a < kmin ? a : kmin;
+			kmax = b > kmax ? b : kmax;
+		}
+		if (lane_id() == 0 && kmin <= kmax) {
+			atomicMin(&minmax[0], kmin);
+			atomicMax(&minmax[1], kmax);
+		}
+	}
 }
 
 // Output arrays of every destination (kernel parameter, 1 KiB).
@@ -81,7 +100,7 @@ struct RouteCfg {
 // The bin -> destination table (4 KiB at 12 bits) is read through L1.
 template <int ND>
 __global__ void __launch_bounds__(ROUTE_THREADS, ND <= 16 ? 3 : 2)
-route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, int bits,
+route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, int bits, uint32_t origin,
 	     const uint8_t *__restrict__ bin_to_dest, int ndest, uint32_t *cursors, const RouteDst dst)
 {
 	constexpr int THREADS = ROUTE_THREADS, ITEMS = ROUTE_ITEMS;
@@ -145,8 +164,8 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 			for (int jj = 0; jj < ITEMS / 2; ++jj) {
 				const ulonglong2 v = k2[jj * THREADS + tid];
 				const uint32_t s0 = (jj * THREADS + tid) * 2;
-				dr[2 * jj] = s0 < count ? uint32_t(__ldg(bin_to_dest + (uint32_t(v.x >> shift) & dmask))) : ND + lane;
-				dr[2 * jj + 1] = s0 + 1 < count ? uint32_t(__ldg(bin_to_dest + (uint32_t(v.y >> shift) & dmask))) : ND + lane;
+				dr[2 * jj] = s0 < count ? uint32_t(__ldg(bin_to_dest + ((uint32_t(v.x >> shift) - origin) & dmask))) : ND + lane;
+				dr[2 * jj + 1] = s0 + 1 < count ? uint32_t(__ldg(bin_to_dest + ((uint32_t(v.y >> shift) - origin) & dmask))) : ND + lane;
 			}
 		}
 		tile_ranks<ITEMS, ND>(cnt, dr);
@@ -185,7 +204,7 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 			if (s != 0xffffu) {
 				const uint64_t key = kin[s];
 				const uint64_t rid = rin[s];
-				const uint32_t d = __ldg(bin_to_dest + (uint32_t(key >> shift) & dmask));
+				const uint32_t d = __ldg(bin_to_dest + ((uint32_t(key >> shift) - origin) & dmask));
 				const uint32_t at = delta[d] + p;
 				st_stream_u64(okeys[d] + at, key);
 				st_stream_u64(orids[d] + at, rid);

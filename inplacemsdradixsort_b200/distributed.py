@@ -4,8 +4,13 @@ The role of the reference's cross-NUMA-node phase (sample -> range histogram ->
 partition into per-node ranges -> every thread sorts its range; msb_64.c:1546-1606,
 1674-2198), re-thought for GPUs connected by NVLink/NVSwitch:
 
-    1. every rank histograms the top `bits` bits of its keys         (device kernel)
+    1. every rank histograms the top `bits` bits of its keys and notes its smallest and
+       largest key                                                    (device kernel)
     2. the histograms are all-gathered                                (NCCL)
+       -- if that cut would overload a rank because the keys share a long prefix (only low
+       bits significant, a narrow value range), steps 1-2 are repeated once on a window
+       placed on the keys' real span [global min, global max] (the reference reaches the
+       same end with delimiters sampled from the data, msb_64.c:239-351)
     3. every rank cuts the bin axis into `world` contiguous ranges of near-equal
        global count -- all ranks compute the same cut from the same data, so no
        further agreement step is needed; the same table gives every send and
@@ -105,12 +110,13 @@ class CudaOps:
         nbytes = _m.workspace_bytes(cap)
         return self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device), nbytes
 
-    def digit_histogram(self, keys, n, shift, bits, out):
-        _m._raise(self.lib.msb64_b200_digit_histogram(keys.data_ptr(), n, shift, bits,
-                                                      out.data_ptr(), self._stream()))
+    def digit_histogram(self, keys, n, shift, bits, origin, out, minmax):
+        """out[0 : 2^bits] = counts of ((key >> shift) - origin) & mask; minmax[0:2] = min, max key."""
+        _m._raise(self.lib.msb64_b200_digit_histogram(keys.data_ptr(), n, shift, bits, origin,
+                                                      out.data_ptr(), minmax.data_ptr(), self._stream()))
 
-    def route(self, keys, rids, n, shift, bits, table, world, cursors, out_keys, out_rids):
-        _m._raise(self.lib.msb64_b200_route(keys.data_ptr(), rids.data_ptr(), n, shift, bits,
+    def route(self, keys, rids, n, shift, bits, origin, table, world, cursors, out_keys, out_rids):
+        _m._raise(self.lib.msb64_b200_route(keys.data_ptr(), rids.data_ptr(), n, shift, bits, origin,
                                             table.data_ptr(), world, cursors.data_ptr(),
                                             out_keys.data_ptr(), out_rids.data_ptr(), self._stream()))
 
@@ -138,10 +144,10 @@ class CudaOps:
     def ipc_close(self, ptr):
         self.lib.msb64_b200_ipc_close(ptr)
 
-    def route_peer(self, keys, rids, n, shift, bits, table, world, cursors, key_ptrs, rid_ptrs):
+    def route_peer(self, keys, rids, n, shift, bits, origin, table, world, cursors, key_ptrs, rid_ptrs):
         kp = (C.c_void_p * world)(*key_ptrs)
         rp = (C.c_void_p * world)(*rid_ptrs)
-        _m._raise(self.lib.msb64_b200_route_peer(keys.data_ptr(), rids.data_ptr(), n, shift, bits,
+        _m._raise(self.lib.msb64_b200_route_peer(keys.data_ptr(), rids.data_ptr(), n, shift, bits, origin,
                                                  table.data_ptr(), world, cursors.data_ptr(), kp, rp,
                                                  self._stream()))
 
@@ -175,8 +181,11 @@ class ShardedSorter:
             raise _m.Msb64Error(-3, "more than MSB64_MAX_PAIRS pairs per GPU")
         self.ops = ops if ops is not None else CudaOps(device)
         o = self.ops
-        self.hist = o.empty(1 << self.bits)
-        self.all_hist = o.empty(self.world << self.bits)
+        if not 4 <= self.bits <= 12:
+            raise _m.Msb64Error(-2, "bits must be 4..12")
+        self.slots = (2 << self.bits) + 2              # room for the (bits+1)-bit window + min, max
+        self.hist = o.empty(self.slots)
+        self.all_hist = o.empty(self.world * self.slots)
         if exchange not in ("auto", "peer", "nccl"):
             raise _m.Msb64Error(-2, "exchange must be 'auto', 'peer' or 'nccl'")
         self.exchange = "nccl"
@@ -263,18 +272,39 @@ class ShardedSorter:
             self._own = None
 
     # -- steps 1-3
-    def plan(self, keys, n):
-        dist = self.dist
-        self.ops.digit_histogram(keys, n, self.shift, self.bits, self.hist)
+    def _histograms(self, keys, n, shift, bits, origin):
+        """Per-rank histograms [world, 2^bits] of the given digit and the global min / max key."""
+        nb = 1 << bits
+        self.ops.digit_histogram(keys, n, shift, bits, origin, self.hist, self.hist[nb: nb + 2])
         if self.world > 1:
-            dist.all_gather_into_tensor(self.all_hist, self.hist, group=self.group)
+            self.dist.all_gather_into_tensor(self.all_hist, self.hist, group=self.group)
             hists = self.all_hist
         else:
             hists = self.hist
-        h = hists.cpu().numpy().reshape(self.world, 1 << self.bits)       # synchronises
+        h = hists.cpu().numpy().reshape(self.world, self.slots)           # synchronises
+        mm = h[:, nb: nb + 2].view(np.uint64)
+        have = mm[:, 0] <= mm[:, 1]                                       # ranks that hold any key
+        gmin = int(mm[have, 0].min()) if have.any() else 0
+        gmax = int(mm[have, 1].max()) if have.any() else 0
+        return h[:, :nb], gmin, gmax
+
+    def plan(self, keys, n):
+        """Returns (shift, bits, origin, table, counts): digit = ((key >> shift) - origin) &
+        (2^bits - 1), table[digit] = destination rank, counts[src][dst] = pairs to move."""
+        shift, bits, origin = self.shift, self.bits, 0
+        h, gmin, gmax = self._histograms(keys, n, shift, bits, origin)
         table = choose_ranges(h.sum(axis=0), self.world)
         counts = exchange_counts(h, table, self.world)
-        return table, counts
+        if self.world > 1 and np.any(counts.sum(axis=0) > self.recv_caps):
+            # the top bits do not separate the keys: put the window on their real span
+            width = (gmax - gmin).bit_length()
+            shift2 = max(width - self.bits, 0)
+            if shift2 < shift:
+                shift, bits, origin = shift2, self.bits + 1, gmin >> shift2   # digits 0 .. 2^bits (one past: bits + 1)
+                h, _, _ = self._histograms(keys, n, shift, bits, origin)
+                table = choose_ranges(h.sum(axis=0), self.world)
+                counts = exchange_counts(h, table, self.world)
+        return shift, bits, origin, table, counts
 
     def sort(self, keys, rids, n: int | None = None, timed: bool = False):
         """keys, rids: this rank's pairs (8-byte integer tensors on the sorter's device).
@@ -290,7 +320,7 @@ class ShardedSorter:
         n = keys.numel() if n is None else int(n)
         if n > self.capacity:
             raise _m.Msb64Error(-2, f"{n} pairs exceed the sorter's capacity {self.capacity}")
-        table, counts = self.plan(keys, n)
+        shift, bits, origin, table, counts = self.plan(keys, n)
         if ev:
             ev[1].record()
         self.last_counts = counts
@@ -313,7 +343,7 @@ class ShardedSorter:
             starts = counts[: self.rank].sum(axis=0).astype(np.uint32)
             cursors = self.ops.from_numpy(starts.view(np.int32))
             table_d = self.ops.from_numpy(table)
-            self.ops.route_peer(keys, rids, n, self.shift, self.bits, table_d, self.world, cursors,
+            self.ops.route_peer(keys, rids, n, shift, bits, origin, table_d, self.world, cursors,
                                 self._peer_keys, self._peer_rids)
             if ev:
                 ev[2].record()
@@ -322,7 +352,7 @@ class ShardedSorter:
             starts = np.concatenate([[0], np.cumsum(send)[:-1]]).astype(np.uint32)
             cursors = self.ops.from_numpy(starts.view(np.int32))
             table_d = self.ops.from_numpy(table)
-            self.ops.route(keys, rids, n, self.shift, self.bits, table_d, self.world, cursors,
+            self.ops.route(keys, rids, n, shift, bits, origin, table_d, self.world, cursors,
                            self.send_keys, self.send_rids)
             ins, outs = [int(x) for x in send], [int(x) for x in recv]
             dist.all_to_all_single(self.recv_keys[:total], self.send_keys[:n], outs, ins, group=self.group)
@@ -331,8 +361,8 @@ class ShardedSorter:
         # the range partition already fixed
         mine = np.nonzero(table == self.rank)[0]
         if mine.size:
-            key_lo = int(mine[0]) << self.shift
-            key_hi = ((int(mine[-1]) + 1) << self.shift) - 1
+            key_lo = min((origin + int(mine[0])) << shift, (1 << 64) - 1)
+            key_hi = min(((origin + int(mine[-1]) + 1) << shift) - 1, (1 << 64) - 1)
         else:
             key_lo, key_hi = 0, (1 << 64) - 1
         if ev:

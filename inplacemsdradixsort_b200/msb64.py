@@ -115,15 +115,15 @@ def load_library() -> C.CDLL:
     L.msb64_b200_check.restype = C.c_int
     L.msb64_b200_check.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u64p, C.c_void_p]
     L.msb64_b200_digit_histogram.restype = C.c_int
-    L.msb64_b200_digit_histogram.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
-                                             C.c_void_p]
+    L.msb64_b200_digit_histogram.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
     L.msb64_b200_route.restype = C.c_int
-    L.msb64_b200_route.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
-                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.msb64_b200_route.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64,
+                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.msb64_b200_route_peer.restype = C.c_int
-    L.msb64_b200_route_peer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
-                                        C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                        C.c_void_p]
+    L.msb64_b200_route_peer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.c_void_p]
     L.msb64_b200_ipc_export.restype = C.c_int
     L.msb64_b200_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
     L.msb64_b200_ipc_open.restype = C.c_void_p

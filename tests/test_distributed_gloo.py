@@ -43,14 +43,20 @@ class NumpyOps:
         nbytes = 16 * cap + 4096
         return torch.zeros(nbytes, dtype=torch.uint8), nbytes
 
-    def digit_histogram(self, keys, n, shift, bits, out):
-        k = keys[:n].numpy().view(np.uint64)
-        d = (k >> np.uint64(shift)) & np.uint64((1 << bits) - 1)
-        out.copy_(torch.from_numpy(np.bincount(d.astype(np.int64), minlength=1 << bits).astype(np.int64)))
+    @staticmethod
+    def _digit(k, shift, bits, origin):
+        return (((k >> np.uint64(shift)) - np.uint64(origin)) & np.uint64((1 << bits) - 1)).astype(np.int64)
 
-    def route(self, keys, rids, n, shift, bits, table, world, cursors, out_keys, out_rids):
+    def digit_histogram(self, keys, n, shift, bits, origin, out, minmax):
         k = keys[:n].numpy().view(np.uint64)
-        d = ((k >> np.uint64(shift)) & np.uint64((1 << bits) - 1)).astype(np.int64)
+        d = self._digit(k, shift, bits, origin)
+        out[: 1 << bits] = torch.from_numpy(np.bincount(d, minlength=1 << bits).astype(np.int64))
+        mm = np.array([k.min() if n else np.uint64((1 << 64) - 1), k.max() if n else 0], dtype=np.uint64)
+        minmax.copy_(torch.from_numpy(mm.view(np.int64)))
+
+    def route(self, keys, rids, n, shift, bits, origin, table, world, cursors, out_keys, out_rids):
+        k = keys[:n].numpy().view(np.uint64)
+        d = self._digit(k, shift, bits, origin)
         dest = table.numpy()[d]
         order = np.argsort(dest, kind="stable")
         starts = cursors.numpy().view(np.uint32)
@@ -109,9 +115,10 @@ def _run(world, kind, n, fudge=1.5):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("kind", ["uniform", "low24", "sorted"])
+@pytest.mark.parametrize("kind", ["uniform", "low24", "sorted", "midbits", "dup1000"])
 def test_sharded_sort_matches_global_sort(world, kind):
-    res = _run(world, kind, 20_000, fudge=float(world) + 0.5)     # low24 lands on one rank
+    # low24 / midbits: the top 12 bits are equal everywhere, the window moves to the span
+    res = _run(world, kind, 20_000, fudge=1.5)
     assert all(r[0] == "ok" for r in res)
     all_k = np.concatenate([r[3] for r in res])
     all_r = np.concatenate([r[4] for r in res])
@@ -135,8 +142,8 @@ def test_uniform_is_balanced():
 
 
 def test_capacity_error_like_the_reference_assert():
-    # every key falls into one top-bits bin -> one rank would receive everything
-    res = _run(2, "low24", 20_000, fudge=1.25)
+    # all keys equal: they may not be split, one rank would receive everything
+    res = _run(2, "equal", 20_000, fudge=1.25)
     assert all(r[0] == "error" and r[1] == -4 for r in res), "every rank must raise together"
 
 

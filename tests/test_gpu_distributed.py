@@ -32,12 +32,18 @@ def test_digit_histogram(gpu, kind, n, bits, shift):
     lib = gpu.load_library()
     keys = make(kind, n, seed=5)
     dk = _dev(gpu, keys)
-    dh = gpu.DeviceArray(1 << bits)
-    assert lib.msb64_b200_digit_histogram(dk.ptr, n, shift, bits, dh.ptr, None) == 0
+    dh = gpu.DeviceArray((1 << bits) + 2)
+    origin = int(keys.min() >> np.uint64(shift)) if n and kind == "skew" else 0
+    assert lib.msb64_b200_digit_histogram(dk.ptr, n, shift, bits, origin, dh.ptr,
+                                          dh.ptr + 8 * (1 << bits), None) == 0
     got = dh.download()
-    want = np.bincount(((keys >> np.uint64(shift)) & np.uint64((1 << bits) - 1)).astype(np.int64),
-                       minlength=1 << bits).astype(np.uint64)
-    assert np.array_equal(got, want)
+    digit = ((keys >> np.uint64(shift)) - np.uint64(origin)) & np.uint64((1 << bits) - 1)
+    want = np.bincount(digit.astype(np.int64), minlength=1 << bits).astype(np.uint64)
+    assert np.array_equal(got[: 1 << bits], want)
+    if n:
+        assert (int(got[1 << bits]), int(got[(1 << bits) + 1])) == (int(keys.min()), int(keys.max()))
+    else:
+        assert int(got[1 << bits]) > int(got[(1 << bits) + 1])            # "no keys": min > max
 
 
 @pytest.mark.parametrize("kind", ["uniform", "skew", "dup16", "sorted"])
@@ -59,7 +65,7 @@ def test_route_groups_by_destination(gpu, kind, n, ndest):
     dc = gpu.DeviceArray((ndest + 1) // 2 + 1)
     lib.msb64_b200_memcpy_h2d(dc.ptr, starts.ctypes.data, starts.size * 4, None)
     lib.msb64_b200_stream_sync(None)
-    assert lib.msb64_b200_route(dk.ptr, dr.ptr, n, shift, bits, dt.ptr, ndest, dc.ptr, ok_.ptr, or_.ptr, None) == 0
+    assert lib.msb64_b200_route(dk.ptr, dr.ptr, n, shift, bits, 0, dt.ptr, ndest, dc.ptr, ok_.ptr, or_.ptr, None) == 0
     gk, gr = ok_.download(), or_.download()
     cur = np.zeros(dc.count, dtype=np.uint64)
     dc.download(cur)
@@ -137,7 +143,7 @@ def _nccl_worker(rank, world, port, kind, n, exchange, result):
 
 
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])
-@pytest.mark.parametrize("kind", ["uniform", "sorted"])
+@pytest.mark.parametrize("kind", ["uniform", "sorted", "low24", "midbits"])
 def test_sharded_sorter_two_gpus_nccl(gpu, kind, exchange):
     import torch
     import torch.multiprocessing as mp

@@ -18,7 +18,7 @@ ok, orr = torch.empty_like(k), torch.empty_like(r)
 st = torch.cuda.current_stream().cuda_stream
 lib.msb64_b200_fill(k.data_ptr(), r.data_ptr(), n, 0, 1, 0, st)
 hist = torch.zeros(4096, dtype=torch.int64, device=dev)
-lib.msb64_b200_digit_histogram(k.data_ptr(), n, 52, 12, hist.data_ptr(), st)
+lib.msb64_b200_digit_histogram(k.data_ptr(), n, 52, 12, 0, hist.data_ptr(), None, st)
 h = hist.cpu().numpy()
 for ndest in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["1", "2", "4", "8", "64"])]:
     table = (np.arange(4096) * ndest // 4096).astype(np.uint8)
@@ -30,7 +30,7 @@ for ndest in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else 
         cur = torch.from_numpy(starts.view(np.int32).copy()).to(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        rc = lib.msb64_b200_route(k.data_ptr(), r.data_ptr(), n, 52, 12, td.data_ptr(), ndest, cur.data_ptr(),
+        rc = lib.msb64_b200_route(k.data_ptr(), r.data_ptr(), n, 52, 12, 0, td.data_ptr(), ndest, cur.data_ptr(),
                                   ok.data_ptr(), orr.data_ptr(), st)
         b.record()
         torch.cuda.synchronize()
