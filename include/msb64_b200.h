@@ -122,6 +122,13 @@ int msb64_b200_sort_device_range(uint64_t *d_keys, uint64_t *d_rids, uint64_t n,
  * default choice for later calls (count = 0 restores the default). */
 int msb64_b200_get_schedule(uint64_t n, int *bits);
 int msb64_b200_set_schedule(const int *bits, int count);
+/* The schedule msb64_b200_sort_device_range uses for keys in [key_lo, key_hi]: digit widths
+ * in bits[] (returns their number), position of the first digit in *shift0 and its origin
+ * (key_lo >> shift0) in *origin0: first digit = (key >> shift0) - origin0, the digits below
+ * are plain bit fields under shift0 (the last one may reach below bit 0's worth of key bits:
+ * its surplus high bits are bits the level above already consumed).  Needs no device. */
+int msb64_b200_get_range_schedule(uint64_t n, uint64_t key_lo, uint64_t key_hi, int *bits,
+				  int *shift0, uint64_t *origin0);
 
 /* Tuning / introspection. */
 int msb64_b200_device_count(void);

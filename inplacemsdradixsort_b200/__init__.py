@@ -8,14 +8,14 @@ that would sort fails loudly when the library or a device is missing.
 """
 from .msb64 import (  # noqa: F401
     DeviceArray, EXPORTS, MSB64_MAX_PAIRS, Msb64Error, check, device_count, fill,
-    free_pinned, get_schedule, last_level_times, last_stats, launch_count, library_path, load_library,
+    free_pinned, get_range_schedule, get_schedule, last_level_times, last_stats, launch_count, library_path, load_library,
     mafree, mamalloc, pinned, set_schedule, sort, sort_device, sort_pairs, sort_tensors,
     workspace_bytes,
 )
 
 __all__ = [
     "DeviceArray", "EXPORTS", "MSB64_MAX_PAIRS", "Msb64Error", "check", "device_count",
-    "fill", "free_pinned", "get_schedule", "last_level_times", "last_stats", "launch_count", "library_path",
+    "fill", "free_pinned", "get_range_schedule", "get_schedule", "last_level_times", "last_stats", "launch_count", "library_path",
     "load_library", "mafree", "mamalloc", "pinned", "set_schedule", "sort", "sort_device",
     "sort_pairs", "sort_tensors", "workspace_bytes",
 ]

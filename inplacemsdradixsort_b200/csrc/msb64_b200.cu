@@ -657,6 +657,18 @@ int msb64_b200_get_schedule(uint64_t n, int *bits)
 	return int(s.size());
 }
 
+int msb64_b200_get_range_schedule(uint64_t n, uint64_t key_lo, uint64_t key_hi, int *bits, int *shift0,
+				  uint64_t *origin0)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	if (key_hi < key_lo || !bits) return 0;
+	const RangePlan r = plan_range(n, key_lo, key_hi);
+	for (size_t i = 0; i < r.sched.size(); ++i) bits[i] = r.sched[i];
+	if (shift0) *shift0 = r.shift0;
+	if (origin0) *origin0 = r.origin0;
+	return int(r.sched.size());
+}
+
 int msb64_b200_set_schedule(const int *bits, int count)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);

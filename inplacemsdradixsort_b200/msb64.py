@@ -32,7 +32,7 @@ ERRORS = {-1: "CUDA", -2: "ARG", -3: "TOO_BIG", -4: "CAPACITY", -5: "NOMEM", -6:
 EXPORTS = (
     "sort", "mamalloc", "msb64_b200_sort", "msb64_b200_sort_host",
     "msb64_b200_workspace_bytes", "msb64_b200_sort_device", "msb64_b200_sort_device_range",
-    "msb64_b200_get_schedule",
+    "msb64_b200_get_schedule", "msb64_b200_get_range_schedule",
     "msb64_b200_set_schedule", "msb64_b200_device_count", "msb64_b200_last_error",
     "msb64_b200_launch_count", "msb64_b200_last_stats", "msb64_b200_last_level_times",
     "msb64_b200_host_alloc",
@@ -88,6 +88,9 @@ def load_library() -> C.CDLL:
                                                C.c_size_t, C.c_void_p, _u64p, C.c_uint64, C.c_uint64]
     L.msb64_b200_get_schedule.restype = C.c_int
     L.msb64_b200_get_schedule.argtypes = [C.c_uint64, C.POINTER(C.c_int)]
+    L.msb64_b200_get_range_schedule.restype = C.c_int
+    L.msb64_b200_get_range_schedule.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_int),
+                                                C.POINTER(C.c_int), _u64p]
     L.msb64_b200_set_schedule.restype = C.c_int
     L.msb64_b200_set_schedule.argtypes = [C.POINTER(C.c_int), C.c_int]
     L.msb64_b200_device_count.restype = C.c_int
@@ -354,6 +357,17 @@ def get_schedule(n: int) -> list[int]:
     bits = (C.c_int * 16)()
     k = load_library().msb64_b200_get_schedule(n, bits)
     return [int(bits[i]) for i in range(k)]
+
+
+def get_range_schedule(n: int, key_lo: int, key_hi: int):
+    """(digit widths, shift of the first digit, origin of the first digit) of a sort whose
+    keys are known to lie in [key_lo, key_hi] (host logic only, no device needed)."""
+    bits = (C.c_int * 32)()
+    shift0 = C.c_int()
+    origin0 = C.c_uint64()
+    k = load_library().msb64_b200_get_range_schedule(n, key_lo, key_hi, bits, C.byref(shift0),
+                                                     C.byref(origin0))
+    return [int(bits[i]) for i in range(k)], int(shift0.value), int(origin0.value)
 
 
 def set_schedule(bits: list[int] | None) -> None:

@@ -100,3 +100,30 @@ def test_workspace_bytes(msb):
         assert w >= 2 * 8 * (1 << e) and w > prev
         prev = w
     assert msb.workspace_bytes(1 << 30) < 2.2 * 16 * (1 << 30)
+
+
+def test_range_schedule_invariants(msb):
+    """msb64_b200_sort_device_range's host logic (no device): for any key range the first
+    digit of the largest key fits its width, widths stay within the kernels' 4..11 bits, and
+    the digits cover every bit in which two keys of the range can differ."""
+    import random
+    rnd = random.Random(7)
+    cases = [(0, (1 << 64) - 1), (5, 5), (7, 8), (0, 1), ((1 << 64) - 2, (1 << 64) - 1),
+             (0x7FFF_FFFF_FFFF_FFFF, 0x8000_0000_0000_0000), (1 << 63, (1 << 64) - 1)]
+    for _ in range(3000):
+        w = rnd.randint(0, 64)
+        lo = rnd.getrandbits(64)
+        span = rnd.getrandbits(w) if w else 0
+        cases.append((lo, min(lo + span, (1 << 64) - 1)))
+    for lo, hi in cases:
+        for n in (2, 5000, 1 << 20, (1 << 30) + 12345, 3 << 30):
+            bits, shift0, origin0 = msb.get_range_schedule(n, lo, hi)
+            assert bits and all(4 <= b <= 11 for b in bits), (lo, hi, n, bits)
+            assert len(bits) <= 16
+            assert 0 <= shift0 <= 64 - 4
+            assert origin0 == lo >> shift0
+            assert (hi >> shift0) - origin0 < (1 << bits[0]), (lo, hi, n, bits, shift0)
+            # the digits below the first one are bit fields under shift0 and must reach bit 0
+            assert sum(bits[1:]) >= shift0, (lo, hi, n, bits, shift0)
+    # the full range reproduces the default schedule
+    assert msb.get_range_schedule(1 << 30, 0, (1 << 64) - 1)[0] == msb.get_schedule(1 << 30)
