@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-child", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -130,7 +131,7 @@ class ReferenceRunner:
         from oracle import oracle as orc
         self.np, self.n = np, n
         self.ref = orc.RefLib()
-        self.fudge = max(1.25, orc.min_fudge(n) + 0.02)
+        self.fudge = max(1.5, orc.min_fudge(n) + 0.05)
         cap = int(n * self.fudge) + 8192
         self.keys, self.rids = self.ref.aligned(cap), self.ref.aligned(cap)
         self.rng = np.random.default_rng(2026)
@@ -150,6 +151,51 @@ class ReferenceRunner:
         return dt
 
 
+def ref_child(sample_n: int, steps: int) -> int:
+    """Hidden mode (--ref-child): the reference in a process of its own, one JSON line per step.
+    The unmodified msb_64.c draws its sample with a seed it never initialises
+    (thread_data_t.seed) and, with its 64 threads oversubscribed on a small host, has been seen
+    to return a misordered pair or to crash once in a few dozen runs -- so it is kept out of
+    the process that holds the GPU results, every step is checked, and the parent retries."""
+    runner = ReferenceRunner(sample_n)
+    for _ in range(steps):
+        try:
+            dt = runner.step()
+            print(json.dumps({"ok": True, "seconds": dt}), flush=True)
+        except AssertionError:
+            print(json.dumps({"ok": False}), flush=True)
+    return 0
+
+
+def run_reference_steps(sample_n: int, steps: int):
+    """`steps` validated reference sorts of sample_n pairs: (seconds per good step, failures)."""
+    good, failed, launches = [], 0, 0
+    while len(good) < steps and launches < steps + 4:
+        launches += 1
+        want = steps - len(good)
+        try:
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-child",
+                                  "--cpu-sample", str(sample_n), "--steps", str(want)],
+                                 capture_output=True, text=True, timeout=600)
+            out = res.stdout
+        except subprocess.TimeoutExpired as e:
+            out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+        seen = 0
+        for line in out.splitlines():
+            try:
+                rec = json.loads(line)
+            except ValueError:
+                continue
+            seen += 1
+            if rec.get("ok"):
+                good.append(float(rec["seconds"]))
+            else:
+                failed += 1
+        if seen < want:
+            failed += 1                                  # the child died inside a step
+    return good, failed
+
+
 def cpu_baseline(sample_n: int, steps: int = 1, warmup: int = 0):
     """The reference msb_64 on the host cores; falls back to the oracle port."""
     import numpy as np
@@ -157,16 +203,18 @@ def cpu_baseline(sample_n: int, steps: int = 1, warmup: int = 0):
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(2026)
     if os.path.exists(orc.REF_SO):
-        runner = ReferenceRunner(sample_n)
-        for _ in range(warmup):
-            runner.step()
-        times = [runner.step() for _ in range(steps)]
-        dt = sum(times) / len(times)
-        return {"value": sample_n / dt / 1e9, "unit": UNIT, "cores": min(64, cores),
-                "kind": "reference",
-                "sample": f"{sample_n} uniform pairs per step, oracle/_ref (unmodified msb_64.c, "
-                          f"64 threads on {cores} host cores), mean of {steps} step(s)",
-                "seconds_per_step": dt}
+        times, failed = run_reference_steps(sample_n, steps + warmup)
+        times = times[warmup:] if len(times) > warmup else times
+        if times:
+            dt = sum(times) / len(times)
+            note = (f"; {failed} further run(s) of the reference failed its own check() or crashed "
+                    f"and were repeated" if failed else "")
+            return {"value": sample_n / dt / 1e9, "unit": UNIT, "cores": min(64, cores),
+                    "kind": "reference",
+                    "sample": f"{sample_n} uniform pairs per step, oracle/_ref (unmodified msb_64.c, "
+                              f"64 threads on {cores} host cores), mean of {len(times)} checked step(s)"
+                              + note,
+                    "seconds_per_step": dt}
     o = orc.Oracle()
     n = min(sample_n, 1 << 22)
     keys = rng.integers(0, 1 << 64, size=n + n // 2 + 64, dtype=np.uint64)
@@ -175,7 +223,8 @@ def cpu_baseline(sample_n: int, steps: int = 1, warmup: int = 0):
     o.sort([keys], [rids], [n])
     dt = time.perf_counter() - t0
     return {"value": n / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{n} uniform pairs, oracle/msb64_oracle.c single thread",
+            "sample": f"{n} uniform pairs, oracle/msb64_oracle.c single thread"
+                      + (" (the compiled reference kept failing)" if os.path.exists(orc.REF_SO) else ""),
             "seconds_per_step": dt}
 
 
@@ -441,4 +490,6 @@ def main_b200(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    if a.ref_child:
+        sys.exit(ref_child(int(eval(a.cpu_sample)), a.steps))
     sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))
