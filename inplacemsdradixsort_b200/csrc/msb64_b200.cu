@@ -98,11 +98,13 @@ std::vector<int> make_schedule(uint64_t n, int width = 64)
 			used += b;
 		}
 	}
-	// the rest of the key (only skewed inputs get here): 8-bit digits, 4..8 bits at the end.
-	// The last digit may reach above `width` (those bits are equal in every key).
+	// the rest of the key (only skewed inputs get here): 7-bit digits, 4..7 bits at the end.
+	// Dead digits cost next to nothing (the plan kernel moves a segment down to its highest
+	// differing bit), so the digits that do get used should be narrow enough for full-speed
+	// scatter passes.  The last digit may reach above `width` (those bits are equal in every key).
 	int rest = width - used;
 	while (rest > 0) {
-		int b = rest <= 8 ? (rest < 4 ? 4 : rest) : (rest < 12 ? rest - rest / 2 : 8);
+		int b = rest <= 7 ? (rest < 4 ? 4 : rest) : (rest < 11 ? rest - rest / 2 : 7);
 		s.push_back(b);
 		rest -= b;
 	}
@@ -232,7 +234,7 @@ int ensure_events()
 
 // ------------------------------------------------------------------ workspace
 struct Layout {
-	size_t keys_b, rids_b, segs[2], tiles[2], hist[2], units, copies, ctl, fused, total;
+	size_t keys_b, rids_b, segs[2], tiles[2], hist[2], segbits[2], units, copies, ctl, fused, total;
 	uint32_t max_segs, max_tiles, max_units, max_copies;
 };
 
@@ -253,6 +255,7 @@ Layout make_layout(uint64_t n, const std::vector<int> &sched)
 	for (int i = 0; i < 2; ++i) L.segs[i] = take(size_t(L.max_segs) * sizeof(Seg));
 	for (int i = 0; i < 2; ++i) L.tiles[i] = take(size_t(L.max_tiles) * sizeof(Tile));
 	for (int i = 0; i < 2; ++i) L.hist[i] = take((size_t(L.max_segs) << maxbits) * 4);
+	for (int i = 0; i < 2; ++i) L.segbits[i] = take(size_t(L.max_segs) * sizeof(SegBits));
 	L.units = take(size_t(L.max_units) * sizeof(Unit));
 	L.copies = take(size_t(L.max_copies) * sizeof(CopyTile));
 	L.ctl = take(sizeof(Control));
@@ -263,7 +266,7 @@ Layout make_layout(uint64_t n, const std::vector<int> &sched)
 
 // ------------------------------------------------------------------ launches
 template <int BITS>
-void launch_level(const Ctx &c, int level, int shift, uint32_t origin, int next_bits, cudaStream_t st,
+void launch_level(const Ctx &c, int level, int shift0, uint32_t origin, int next_bits, cudaStream_t st,
 		  cudaEvent_t *ev)
 {
 	using H = HistCfg<BITS, 256>;
@@ -272,19 +275,19 @@ void launch_level(const Ctx &c, int level, int shift, uint32_t origin, int next_
 	// level 0 is one segment: its histogram pass also counts the level-1 digits per bin
 	// (32 KiB of shared counters), and level 1 needs no histogram pass
 	const bool fuse = level == 0 && next_bits > 0 && BITS + next_bits <= FUSE_MAX_BITS &&
-			  BITS < FUSE_MAX_BITS - 3 && g_dev.fused_blocks[BITS] > 0 && shift >= next_bits && !g_no_fuse;
+			  BITS < FUSE_MAX_BITS - 3 && g_dev.fused_blocks[BITS] > 0 && shift0 >= next_bits && !g_no_fuse;
 	if (fuse) {
 		const size_t smem = H::SMEM + (size_t(H::NB + 32) << next_bits) * 4;
 		histogram_kernel<BITS, 256, true><<<g_dev.sms * g_dev.fused_blocks[BITS], 256, smem, st>>>(
-			c, level, shift, origin, shift - next_bits, next_bits);
+			c, level, origin, next_bits);
 	} else {
 		histogram_kernel<BITS, 256, false><<<g_dev.sms * g_dev.hist_blocks[BITS], 256, H::SMEM, st>>>(
-			c, level, shift, origin, 0, 0);
+			c, level, origin, 0);
 	}
 	if (ev) cudaEventRecord(ev[1], st);
-	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits, shift, fuse);
+	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits, fuse);
 	if (ev) cudaEventRecord(ev[2], st);
-	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<g_dev.sms * g_dev.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, shift, origin);
+	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<g_dev.sms * g_dev.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, origin);
 	if (ev) cudaEventRecord(ev[3], st);
 	g_launches += 3;
 }
@@ -326,6 +329,7 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 		c.segs[i] = reinterpret_cast<Seg *>(w + L.segs[i]);
 		c.tiles[i] = reinterpret_cast<Tile *>(w + L.tiles[i]);
 		c.hist[i] = reinterpret_cast<uint32_t *>(w + L.hist[i]);
+		c.segbits[i] = reinterpret_cast<SegBits *>(w + L.segbits[i]);
 	}
 	c.units = reinterpret_cast<Unit *>(w + L.units);
 	c.copies = reinterpret_cast<CopyTile *>(w + L.copies);
@@ -344,13 +348,14 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	}
 	const int levels = int(sched.size());
 	if (ev) cudaEventRecord(ev[0], st);
-	init_kernel<<<g_dev.sms, 256, 0, st>>>(c, sched[0]);
+	init_kernel<<<g_dev.sms, 256, 0, st>>>(c, sched[0], rp.shift0);
 	g_launches += 1;
 	if (n > LOCAL_CAP) {
-		int shift = rp.shift0 + sched[0];
+		// the position of a segment's digit travels with the segment (msb64_plan.cuh); the
+		// host only says where level 0 starts
 		for (int l = 0; l < levels; ++l) {
 			const int bits = sched[l];
-			shift = shift > bits ? shift - bits : 0;
+			const int shift = rp.shift0;
 			const uint32_t origin = l == 0 ? uint32_t(rp.origin0) : 0u;
 			const int next_bits = l + 1 < levels ? sched[l + 1] : 0;
 			cudaEvent_t *lev = ev ? ev + 1 + 4 * l : nullptr;
@@ -372,9 +377,9 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	// units whose keys leave room for a slot number in one word take the packed path, the rest
 	// (small arrays, very deep levels never) the general one; an empty list costs a launch
 	local_sort_packed_kernel<<<g_dev.sms * g_dev.packed_blocks, LOCAL_THREADS, PACKED_SMEM, st>>>(
-		c, uint32_t(rp.shift0), rp.origin0 << rp.shift0);
+		c, rp.origin0 << rp.shift0);
 	local_sort_kernel<<<g_dev.sms * g_dev.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(
-		c, uint32_t(rp.shift0), rp.origin0 << rp.shift0);
+		c, rp.origin0 << rp.shift0);
 	g_launches += 1;
 	if (tail) cudaEventRecord(tail[1], st);
 	copy_kernel<<<g_dev.sms * 8, 256, 0, st>>>(c);

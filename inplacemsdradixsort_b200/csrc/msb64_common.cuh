@@ -38,10 +38,25 @@ struct Seg {
 	uint32_t begin;   // first element
 	uint32_t size;    // > LOCAL_CAP by construction
 	uint32_t buf;     // buffer holding it now (0 = A, 1 = B)
-	uint32_t skip;    // SEG_SKIP: every key has the same digit, nothing to move (set by this level's plan);
-	                  // SEG_HIST_READY: the histogram was computed by the level above (fused pass)
+	uint32_t flags;   // SEG_* bits | position of the segment's digit << 8
 };
-constexpr uint32_t SEG_SKIP = 1u, SEG_HIST_READY = 2u;
+// SEG_SKIP: every key has the same digit, nothing to move (set by this level's plan);
+// SEG_HIST_READY: the histogram was computed by the level above (fused pass);
+// SEG_WANT_BITS: the histogram pass also accumulates OR / AND of the segment's keys (asked
+// for by the plan kernel when the level above found the segment's digit degenerate).
+constexpr uint32_t SEG_SKIP = 1u, SEG_HIST_READY = 2u, SEG_WANT_BITS = 4u;
+// The digit a segment is partitioned on is (key >> shift) & (2^bits - 1): the width comes from
+// the level (schedule), the POSITION is the segment's own -- a segment whose keys agree on
+// more bits than the schedule assumes (low-entropy keys) is moved down to its highest
+// differing bit by the plan kernel instead of paying one histogram pass per dead digit.
+__host__ __device__ inline uint32_t seg_flags(int shift, uint32_t f) { return (uint32_t(shift) << 8) | f; }
+__host__ __device__ inline int seg_shift(uint32_t flags) { return int((flags >> 8) & 63u); }
+
+// OR and AND of a segment's keys, accumulated by the histogram pass of SEG_WANT_BITS segments:
+// OR & ~AND = the bits in which its keys differ.
+struct SegBits {
+	unsigned long long vor, vand;
+};
 
 struct Tile {
 	uint32_t seg;     // index into this level's Seg list
@@ -59,15 +74,17 @@ struct Unit {
 // digit at bit position `shift`: its keys lie in a contiguous key range that starts at
 // prefix | first << shift and agree on every bit above shift + bits.  The local sort
 // subtracts that origin so that the keys of a unit made of several buckets spread evenly
-// over its counting bins.  origin word: shift [0,6) | bits [6,10) | first digit [10,22);
+// over its counting bins.  origin word: shift [0,6) | bits [6,10) | first digit [10,22) |
+// bit 22: filed at level 0 (digits relative to the sort's key_lo, see msb64_b200.cu);
 // bits = 0: nothing is known about the unit's keys (a whole small array).
-__host__ __device__ inline uint32_t unit_origin(int shift, uint32_t first_digit, int bits)
+constexpr uint32_t UNIT_LEVEL0 = 1u << 22;
+__host__ __device__ inline uint32_t unit_origin(int shift, uint32_t first_digit, int bits, bool level0)
 {
-	return uint32_t(shift) | (uint32_t(bits) << 6) | (first_digit << 10);
+	return uint32_t(shift) | (uint32_t(bits) << 6) | (first_digit << 10) | (level0 ? UNIT_LEVEL0 : 0u);
 }
 __host__ __device__ inline uint64_t unit_origin_key(uint32_t origin)
 {
-	return uint64_t(origin >> 10) << (origin & 63u);
+	return uint64_t((origin >> 10) & 0xfffu) << (origin & 63u);
 }
 
 struct CopyTile {
@@ -96,6 +113,7 @@ struct Ctx {
 	Seg *segs[2];            // ping-pong by level parity
 	Tile *tiles[2];
 	uint32_t *hist[2];       // [seg][bin] counts, turned into write cursors by plan
+	SegBits *segbits[2];     // OR / AND of every segment's keys
 	Unit *units;
 	CopyTile *copies;
 	Control *ctl;

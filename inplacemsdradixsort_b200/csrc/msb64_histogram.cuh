@@ -20,7 +20,7 @@ template <int BITS, int THREADS>
 struct HistCfg {
 	static constexpr int NB = 1 << BITS;
 	static constexpr int ITEMS = TILE / THREADS;
-	static constexpr size_t SMEM = size_t(NB + 32) * sizeof(uint32_t);   // + per-lane dummy bins
+	static constexpr size_t SMEM = size_t(NB + 32 + 4) * sizeof(uint32_t);   // + per-lane dummy bins + OR / AND words
 };
 
 // The tile's digits of one thread into the shared histogram.  Branch-free hot loop (a
@@ -57,20 +57,22 @@ __device__ __forceinline__ void hist_add_tile(uint32_t *h, const uint64_t (&k)[I
 	}
 }
 
-// FUSE (level 0 only, one segment): fshift / fbits describe the level-1 digit; the counts of
+// For segments flagged SEG_WANT_BITS the pass also accumulates OR and AND of the keys
+// (c.segbits): the plan kernel learns from them where the segment's keys really differ.
+// FUSE (level 0 only, one segment): fbits = width of the level-1 digit (right below this level's); the counts of
 // level-1 digits per level-0 bin go to c.fused and become the children's histograms in the
 // plan kernel, so level 1 needs no histogram pass of its own.
 template <int BITS, int THREADS, bool FUSE>
-__global__ void __launch_bounds__(THREADS)
-histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t origin,
-		 const int fshift, const int fbits)
+__global__ void __launch_bounds__(THREADS, 4)
+histogram_kernel(const Ctx c, const int level, const uint32_t origin, const int fbits)
 {
 	using Cfg = HistCfg<BITS, THREADS>;
 	constexpr int NB = Cfg::NB, ITEMS = Cfg::ITEMS;
 	static_assert(ITEMS % 2 == 0, "tile is loaded as 16-byte pairs");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);     // [NB + 32]
-	uint32_t *sh2 = sh + NB + 32;                              // FUSE: [(NB + 32) << fbits] (dummy rows included)
+	uint32_t *sbits = sh + NB + 32;                            // [4] OR lo, OR hi, AND lo, AND hi of the block's keys
+	uint32_t *sh2 = sbits + 4;                                 // FUSE: [(NB + 32) << fbits] (dummy rows included)
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t ntiles = c.ctl->ntiles[level];
@@ -78,8 +80,45 @@ histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t o
 	const Seg *segs = (level & 1) ? c.segs[1] : c.segs[0];
 	const Tile *tiles = (level & 1) ? c.tiles[1] : c.tiles[0];
 	uint32_t *hist = (level & 1) ? c.hist[1] : c.hist[0];
+	SegBits *segbits = (level & 1) ? c.segbits[1] : c.segbits[0];
+	// OR / AND of the keys this thread has seen of the current segment
+	unsigned long long bor = 0, band = ~0ull;
+	// block histogram and OR / AND words to the segment's global counters (all threads)
+	bool want = false;            // the current segment asked for OR / AND
+	auto flush = [&](uint32_t seg, bool again) {
+		if (want) {
+		const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(bor));
+		const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(bor >> 32));
+		const uint32_t alo = __reduce_and_sync(0xffffffffu, uint32_t(band));
+		const uint32_t ahi = __reduce_and_sync(0xffffffffu, uint32_t(band >> 32));
+		if (lane_id() == 0) {
+			atomicOr(&sbits[0], olo);
+			atomicOr(&sbits[1], ohi);
+			atomicAnd(&sbits[2], alo);
+			atomicAnd(&sbits[3], ahi);
+		}
+		bor = 0;
+		band = ~0ull;
+		}
+		__syncthreads();
+		for (int b = tid; b < NB; b += THREADS) {
+			const uint32_t v = sh[b];
+			if (v) {
+				atomicAdd(&hist[size_t(seg) * NB + b], v);
+				sh[b] = 0;
+			}
+		}
+		if (want && tid == 0) {
+			atomicOr(&segbits[seg].vor, ((unsigned long long) sbits[1] << 32) | sbits[0]);
+			atomicAnd(&segbits[seg].vand, ((unsigned long long) sbits[3] << 32) | sbits[2]);
+			sbits[0] = sbits[1] = 0u;
+			sbits[2] = sbits[3] = 0xffffffffu;
+		}
+		if (again) __syncthreads();
+	};
 
 	for (int i = tid; i < NB + 32; i += THREADS) sh[i] = 0;
+	if (tid < 4) sbits[tid] = tid < 2 ? 0u : 0xffffffffu;
 	if (FUSE)
 		for (int i = tid; i < ((NB + 32) << fbits); i += THREADS) sh2[i] = 0;
 	__syncthreads();
@@ -88,21 +127,13 @@ histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t o
 	for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
 		const Tile tile = tiles[t];
 		if (tile.seg != cur_seg) {
-			if (cur_seg != 0xffffffffu) {
-				__syncthreads();
-				for (int b = tid; b < NB; b += THREADS) {
-					const uint32_t v = sh[b];
-					if (v) {
-						atomicAdd(&hist[size_t(cur_seg) * NB + b], v);
-						sh[b] = 0;
-					}
-				}
-				__syncthreads();
-			}
+			if (cur_seg != 0xffffffffu) flush(cur_seg, true);
 			cur_seg = tile.seg;
 		}
 		const Seg s = segs[tile.seg];
-		if (s.skip & SEG_HIST_READY) continue;             // counted by the fused pass of the level above
+		want = (s.flags & (SEG_WANT_BITS | SEG_HIST_READY)) == SEG_WANT_BITS;
+		if (s.flags & SEG_HIST_READY) continue;            // counted by the fused pass of the level above
+		const int shift = seg_shift(s.flags);
 		const uint64_t *keys = s.buf ? c.keys[1] : c.keys[0];
 		const uint32_t end = s.begin + s.size;
 		const uint32_t lo = seg_tile_origin(s.begin) + tile.idx * TILE;
@@ -127,14 +158,18 @@ histogram_kernel(const Ctx c, const int level, const int shift, const uint32_t o
 				validmask |= uint32_t(valid) << j;
 			}
 		}
-		hist_add_tile<ITEMS, NB, FUSE>(sh, k, shift, origin, validmask, sh2, fshift, fbits);
+		if (want) {
+#pragma unroll
+			for (int j = 0; j < ITEMS; ++j)
+				if ((validmask >> j) & 1u) {
+					bor |= k[j];
+					band &= k[j];
+				}
+		}
+		hist_add_tile<ITEMS, NB, FUSE>(sh, k, shift, origin, validmask, sh2, shift - fbits, fbits);
 	}
 	if (cur_seg != 0xffffffffu) {
-		__syncthreads();
-		for (int b = tid; b < NB; b += THREADS) {
-			const uint32_t v = sh[b];
-			if (v) atomicAdd(&hist[size_t(cur_seg) * NB + b], v);
-		}
+		flush(cur_seg, false);
 		if (FUSE)
 			for (int i = tid; i < (NB << fbits); i += THREADS) {
 				const uint32_t v = sh2[i];

@@ -62,7 +62,7 @@ __device__ __forceinline__ void block_bitonic1(uint64_t *k, const uint32_t n)
 }
 
 __global__ void __launch_bounds__(LOCAL_THREADS, LOCAL_MINB)
-local_sort_packed_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_key)
+local_sort_packed_kernel(const Ctx c, const uint64_t base_key)
 {
 	constexpr int THREADS = LOCAL_THREADS, ITEMS = LOCAL_ITEMS, WARPS = THREADS / 32;
 	constexpr int OWNERS = LOCAL_OWNERS;
@@ -115,7 +115,7 @@ local_sort_packed_kernel(const Ctx c, const uint32_t base_shift, const uint64_t 
 				b4[i] = make_uint4(0u, 0u, 0u, 0u);
 		}
 		if (tid == 0) s_nbig = 0;
-		const uint64_t origin = unit_origin_key(un.origin) + ((un.origin & 63u) == base_shift ? base_key : 0ull);
+		const uint64_t origin = unit_origin_key(un.origin) + ((un.origin & UNIT_LEVEL0) ? base_key : 0ull);
 		uint64_t vor = k[0] - origin, vand = vor;
 #pragma unroll
 		for (int j = 1; j < ITEMS; ++j)

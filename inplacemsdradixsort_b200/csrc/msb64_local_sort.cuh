@@ -76,7 +76,7 @@ __device__ __forceinline__ void block_bitonic(uint64_t *k, uint64_t *r, const ui
 }
 
 __global__ void __launch_bounds__(LOCAL_THREADS, LOCAL_MINB)
-local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_key)
+local_sort_kernel(const Ctx c, const uint64_t base_key)
 {
 	constexpr int THREADS = LOCAL_THREADS, ITEMS = LOCAL_ITEMS, WARPS = THREADS / 32;
 	constexpr int OWNERS = LOCAL_OWNERS;
@@ -134,7 +134,7 @@ local_sort_kernel(const Ctx c, const uint32_t base_shift, const uint64_t base_ke
 		if (tid == 0) s_nbig = 0;
 		// binning value: key minus the unit's origin (monotone; see unit_origin)
 		// units filed at level 0 of a range-limited sort carry digits relative to base_key
-		const uint64_t origin = unit_origin_key(un.origin) + ((un.origin & 63u) == base_shift ? base_key : 0ull);
+		const uint64_t origin = unit_origin_key(un.origin) + ((un.origin & UNIT_LEVEL0) ? base_key : 0ull);
 		uint64_t vor = k[0] - origin, vand = vor;
 #pragma unroll
 		for (int j = 1; j < ITEMS; ++j)

@@ -22,7 +22,7 @@ namespace msb64 {
 constexpr int PLAN_THREADS = 256;
 
 // First kernel of a sort: control block, level-0 segment, its tiles and histogram.
-__global__ void init_kernel(const Ctx c, const int bits0)
+__global__ void init_kernel(const Ctx c, const int bits0, const int shift0)
 {
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t gsize = gridDim.x * blockDim.x;
@@ -45,7 +45,8 @@ __global__ void init_kernel(const Ctx c, const int bits0)
 		if (c.n > LOCAL_CAP) {
 			ctl->nsegs[0] = 1;
 			ctl->ntiles[0] = nt;
-			c.segs[0][0] = Seg{0u, c.n, 0u, 0u};
+			c.segs[0][0] = Seg{0u, c.n, 0u, seg_flags(shift0, 0u)};
+			c.segbits[0][0] = SegBits{0ull, ~0ull};
 		} else if (c.n > 0) {
 			ctl->nslow = 1;                                  // nothing known about the keys: general path
 			c.units[c.max_units - 1] = Unit{0u, c.n, 0u, 0u};
@@ -69,11 +70,12 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v)
 }
 
 // Whole warp: make [begin, begin+size) in buffer `buf` a segment of level+1.
+// shift: position of the digit the child is partitioned on at the next level;
 // ready: the child's histogram (nbn counts) was computed by the fused pass, or NULL.
 __device__ __forceinline__ void emit_segment(const Ctx &c, Control *ctl, Seg *segs_out,
 					     Tile *tiles_out, uint32_t *hist_out, int level,
 					     uint32_t nbn, uint32_t begin, uint32_t size, uint32_t buf,
-					     const uint32_t *ready = nullptr)
+					     int shift, const uint32_t *ready = nullptr, uint32_t more_flags = 0)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t nt = seg_tile_count(begin, size);
@@ -82,7 +84,10 @@ __device__ __forceinline__ void emit_segment(const Ctx &c, Control *ctl, Seg *se
 		child = atomicAdd(&ctl->nsegs[level + 1], 1u);
 		tile_at = atomicAdd(&ctl->ntiles[level + 1], nt);
 		if (child >= c.max_segs) atomicOr(&ctl->error, 1u);
-		else segs_out[child] = Seg{begin, size, buf, ready ? SEG_HIST_READY : 0u};
+		else {
+			segs_out[child] = Seg{begin, size, buf, seg_flags(shift, (ready ? SEG_HIST_READY : 0u) | more_flags)};
+			((level & 1) ? c.segbits[0] : c.segbits[1])[child] = SegBits{0ull, ~0ull};
+		}
 		if (tile_at + nt > c.max_tiles) atomicOr(&ctl->error, 2u);
 		if (ready) atomicAdd(&ctl->nready[level + 1], 1u);
 		else atomicAdd(&ctl->hist_keys, (unsigned long long) size);
@@ -128,11 +133,19 @@ __device__ __forceinline__ void emit_copy(const Ctx &c, Control *ctl, uint32_t b
 }
 
 // bits: digit width of this level; next_bits: of the next level (0 = this is the last);
-// shift: position of this level's digit in the key; fused: c.fused holds the next level's digit
-// counts per bin of this level (level 0 only).
+// fused: c.fused holds the next level's digit counts per bin of this level (level 0 only).
+//
+// A segment whose digit is degenerate (all keys in one bin) moves to the next level as it is,
+// flagged SEG_WANT_BITS: that level's histogram pass then also accumulates OR / AND of its
+// keys (c.segbits), and if its digit is degenerate again the plan kernel knows where the
+// keys really differ:
+//   - nowhere (all keys equal): the segment is finished, nothing below can separate them;
+//   - otherwise it goes on with its digit placed right below its highest differing bit,
+//     however many bits further down that is.
+// Presorted, low-entropy and duplicate-heavy inputs pay two histogram passes for a run of
+// dead digits, not one per digit; inputs without degenerate digits pay nothing.
 __global__ void __launch_bounds__(PLAN_THREADS)
-plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, const int shift,
-	    const bool fused)
+plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, const bool fused)
 {
 	const uint32_t lane = lane_id();
 	const uint32_t warps_per_block = PLAN_THREADS / 32;
@@ -143,13 +156,17 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 	Tile *tiles_out = (level & 1) ? c.tiles[0] : c.tiles[1];
 	uint32_t *hist = (level & 1) ? c.hist[1] : c.hist[0];
 	uint32_t *hist_out = (level & 1) ? c.hist[0] : c.hist[1];
+	const SegBits *segbits = (level & 1) ? c.segbits[1] : c.segbits[0];
 	const uint32_t nsegs = min(ctl->nsegs[level], c.max_segs);
-	const bool last = next_bits == 0;
 
 	for (uint32_t sg = blockIdx.x * warps_per_block + (threadIdx.x >> 5); sg < nsegs;
 	     sg += gridDim.x * warps_per_block) {
 		const Seg s = segs[sg];
 		uint32_t *h = hist + size_t(sg) * NB;
+		const int shift = seg_shift(s.flags);
+		// no digit below this one: the keys of a bin are equal, every bucket is final
+		const bool last = next_bits == 0 || shift == 0;
+		const int child_shift = shift > next_bits ? shift - next_bits : 0;
 
 		// pass 1: is the digit degenerate (one bin holds the whole segment)?
 		uint32_t mx = 0;
@@ -157,20 +174,32 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 		mx = __reduce_max_sync(0xffffffffu, mx);
 		if (mx == s.size) {
 			if (lane == 0) {
-				segs[sg].skip = s.skip | SEG_SKIP;
+				segs[sg].flags = s.flags | SEG_SKIP;
 				atomicAdd(&ctl->degenerate, 1u);
 			}
-			if (!last) {
-				// the one non-empty bin (for the fused histogram's row)
-				uint32_t full_bin = 0;
-				for (uint32_t b = lane; b < NB; b += 32)
-					if (h[b] == s.size) full_bin = b;
-				full_bin = __reduce_max_sync(0xffffffffu, full_bin);
-				emit_segment(c, ctl, segs_out, tiles_out, hist_out, level, NBN, s.begin, s.size, s.buf,
-					     fused ? c.fused + size_t(full_bin) * NBN : nullptr);
+			// bits in which the segment's keys differ (all below `shift`), if this level's
+			// histogram pass was asked to collect them
+			unsigned long long diff = ~0ull;
+			if ((s.flags & SEG_WANT_BITS) && !(s.flags & SEG_HIST_READY)) {
+				const SegBits sb = segbits[sg];
+				diff = sb.vor & ~sb.vand;
 			}
-			else if (s.buf == 1u)
-				emit_copy(c, ctl, s.begin, s.size);
+			if (last || diff == 0) {
+				if (s.buf == 1u) emit_copy(c, ctl, s.begin, s.size);      // all keys equal: final
+				continue;
+			}
+			// digit of the next level: right below the highest differing bit, or where the
+			// schedule puts it when that is not known
+			int down = child_shift;
+			if (diff != ~0ull) down = min(child_shift, max(63 - __clzll(diff) + 1 - next_bits, 0));
+			// the one non-empty bin (for the fused histogram's row, valid at the schedule's position only)
+			uint32_t full_bin = 0;
+			for (uint32_t b = lane; b < NB; b += 32)
+				if (h[b] == s.size) full_bin = b;
+			full_bin = __reduce_max_sync(0xffffffffu, full_bin);
+			emit_segment(c, ctl, segs_out, tiles_out, hist_out, level, NBN, s.begin, s.size, s.buf, down,
+				     fused && down == child_shift ? c.fused + size_t(full_bin) * NBN : nullptr,
+				     diff == ~0ull ? SEG_WANT_BITS : 0u);
 			continue;
 		}
 		const uint32_t dst_buf = s.buf ^ 1u;
@@ -195,7 +224,7 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 				large &= large - 1;
 				emit_segment(c, ctl, segs_out, tiles_out, hist_out, level, NBN,
 					     __shfl_sync(0xffffffffu, beg, src),
-					     __shfl_sync(0xffffffffu, cnt, src), dst_buf,
+					     __shfl_sync(0xffffffffu, cnt, src), dst_buf, child_shift,
 					     fused ? c.fused + size_t(b0 + src) * NBN : nullptr);
 			}
 			// greedy merge of neighbouring small buckets into units (all lanes in step)
@@ -207,7 +236,7 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 				const uint32_t bb = __shfl_sync(0xffffffffu, beg, src);
 				if (cb > LOCAL_CAP || run_size + cb > LOCAL_CAP) {
 					if (run_size && lane == 0)
-						emit_unit(c, ctl, run_beg, run_size, dst_buf, unit_origin(shift, run_dig, bits));
+						emit_unit(c, ctl, run_beg, run_size, dst_buf, unit_origin(shift, run_dig, bits, level == 0));
 					local_pairs += run_size;
 					run_size = 0;
 					if (cb > LOCAL_CAP) continue;
@@ -221,7 +250,7 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 		}
 		if (!last) {
 			if (run_size && lane == 0)
-				emit_unit(c, ctl, run_beg, run_size, dst_buf, unit_origin(shift, run_dig, bits));
+				emit_unit(c, ctl, run_beg, run_size, dst_buf, unit_origin(shift, run_dig, bits, level == 0));
 			local_pairs += run_size;
 			if (local_pairs && lane == 0) atomicAdd(&ctl->local_pairs, local_pairs);
 		} else if (dst_buf == 1u) {

@@ -52,7 +52,8 @@ struct TileDesc {
 	uint32_t end;     // one past its last
 	uint32_t lo;      // first element slot of the tile (even)
 	uint32_t flags;   // bit 0: source buffer, bit 1: segment skipped, bit 2: no such tile
-	uint32_t pad[3];
+	uint32_t shift;   // position of the segment's digit
+	uint32_t pad[2];
 };
 constexpr uint32_t TD_BUF = 1u, TD_SKIP = 2u, TD_NONE = 4u;
 
@@ -117,7 +118,7 @@ __device__ __forceinline__ void tile_ranks(uint32_t *cnt, uint32_t (&d)[ITEMS])
 
 template <int BITS, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-scatter_kernel(const Ctx c, const int level, const int shift, const uint32_t origin)
+scatter_kernel(const Ctx c, const int level, const uint32_t origin)
 {
 	using Cfg = ScatterCfg<BITS, THREADS>;
 	constexpr int NB = Cfg::NB, ITEMS = Cfg::ITEMS, BPT = Cfg::BPT;
@@ -153,7 +154,8 @@ scatter_kernel(const Ctx c, const int level, const int shift, const uint32_t ori
 		slot->begin = s.begin;
 		slot->end = s.begin + s.size;
 		slot->lo = seg_tile_origin(s.begin) + tile.idx * TILE;
-		slot->flags = (s.buf ? TD_BUF : 0u) | ((s.skip & SEG_SKIP) ? TD_SKIP : 0u);
+		slot->flags = (s.buf ? TD_BUF : 0u) | ((s.flags & SEG_SKIP) ? TD_SKIP : 0u);
+		slot->shift = uint32_t(seg_shift(s.flags));
 	};
 	// thread 0 only: a tile whose whole window lies inside the array is fetched by bulk
 	// copies (slots outside the segment receive the neighbours' data and are ignored)
@@ -191,6 +193,7 @@ scatter_kernel(const Ctx c, const int level, const int shift, const uint32_t ori
 		uint64_t *dst_keys = src_b ? c.keys[0] : c.keys[1];
 		uint64_t *dst_rids = src_b ? c.rids[0] : c.rids[1];
 		const uint32_t lo = cur.lo;
+		const int shift = int(cur.shift);
 		const bool full = lo >= cur.begin && lo + TILE <= cur.end;
 		const uint32_t count = min(lo + TILE, cur.end) - max(lo, cur.begin);
 
