@@ -269,7 +269,7 @@ scatter_kernel(const Ctx c, const int level, const uint32_t origin)
 		__syncthreads();
 
 		// 4. coalesced write-out: position i of the bin-ordered tile goes to delta[bin] + i
-#pragma unroll 4
+#pragma unroll 8
 		for (uint32_t i = tid; i < count; i += THREADS) {
 			const uint32_t s = sidx[i];
 			const uint64_t key = kin[s];
