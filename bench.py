@@ -35,6 +35,22 @@ UNIT = "Gpairs/s"
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md, "of fallback"
 
 
+def parse_count(text) -> int:
+    """'1<<30', '2**30', '3*(1<<28)', '1073741824' ... -> int, without eval()."""
+    import ast
+    import operator as op
+    ops = {ast.LShift: op.lshift, ast.Mult: op.mul, ast.Pow: op.pow, ast.Add: op.add, ast.Sub: op.sub,
+           ast.FloorDiv: op.floordiv}
+
+    def ev(node):
+        if isinstance(node, ast.Constant) and isinstance(node.value, int):
+            return node.value
+        if isinstance(node, ast.BinOp) and type(node.op) in ops:
+            return ops[type(node.op)](ev(node.left), ev(node.right))
+        raise ValueError(f"not a pair count: {text!r}")
+    return int(ev(ast.parse(str(text), mode="eval").body))
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -232,8 +248,8 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample_n = int(eval(args.cpu_sample))
-    per_gpu = int(eval(args.pairs_per_gpu))
+    sample_n = parse_count(args.cpu_sample)
+    per_gpu = parse_count(args.pairs_per_gpu)
     base = cpu_baseline(sample_n, steps=max(args.steps, 1), warmup=max(min(args.warmup, 1), 0))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
@@ -272,7 +288,7 @@ def main_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    n = int(eval(args.pairs_per_gpu))
+    n = parse_count(args.pairs_per_gpu)
     stream = torch.cuda.current_stream().cuda_stream
     lib = m.load_library()
 
@@ -475,7 +491,7 @@ def main_b200(args):
 
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(int(eval(args.cpu_sample))).items()
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(parse_count(args.cpu_sample)).items()
                                     if k != "seconds_per_step"}
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(),
@@ -491,5 +507,5 @@ def main_b200(args):
 if __name__ == "__main__":
     a = parse_args()
     if a.ref_child:
-        sys.exit(ref_child(int(eval(a.cpu_sample)), a.steps))
+        sys.exit(ref_child(parse_count(a.cpu_sample), a.steps))
     sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))
