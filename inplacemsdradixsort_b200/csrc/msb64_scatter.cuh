@@ -157,14 +157,22 @@ scatter_kernel(const Ctx c, const int level, const uint32_t origin)
 		slot->flags = (s.buf ? TD_BUF : 0u) | ((s.flags & SEG_SKIP) ? TD_SKIP : 0u);
 		slot->shift = uint32_t(seg_shift(s.flags));
 	};
-	// thread 0 only: a tile whose whole window lies inside the array is fetched by bulk
-	// copies (slots outside the segment receive the neighbours' data and are ignored)
+	// Slots of a tile's window that bulk copies fetch: up to the segment's end (rounded to the
+	// 16-byte granule), so that the short last tile of a segment does not cost a whole tile
+	// of traffic.  0 = the window would leave the array (last tile only): plain loads instead.
+	auto window = [&](uint32_t lo, uint32_t end) -> uint32_t {
+		const uint32_t w = min(uint32_t(TILE), (end - lo + 1u) & ~1u);
+		return lo + w <= c.n ? w : 0u;
+	};
+	// thread 0 only (slots in front of the segment receive the neighbours' data and are ignored)
 	auto start_copy = [&](const TileDesc &d) {
-		if ((d.flags & (TD_SKIP | TD_NONE)) || d.lo + TILE > c.n) return;
+		if (d.flags & (TD_SKIP | TD_NONE)) return;
+		const uint32_t w = window(d.lo, d.end);
+		if (!w) return;
 		const bool b = d.flags & TD_BUF;
-		mbar_expect_tx(bar, TILE * 16);
-		bulk_copy_g2s(kin, (b ? c.keys[1] : c.keys[0]) + d.lo, TILE * 8, bar);
-		bulk_copy_g2s(rin, (b ? c.rids[1] : c.rids[0]) + d.lo, TILE * 8, bar);
+		mbar_expect_tx(bar, w * 16);
+		bulk_copy_g2s(kin, (b ? c.keys[1] : c.keys[0]) + d.lo, w * 8, bar);
+		bulk_copy_g2s(rin, (b ? c.rids[1] : c.rids[0]) + d.lo, w * 8, bar);
 	};
 
 	if (tid == 0) {
@@ -198,11 +206,11 @@ scatter_kernel(const Ctx c, const int level, const uint32_t origin)
 		const uint32_t count = min(lo + TILE, cur.end) - max(lo, cur.begin);
 
 		// 0. the tile's pairs in shared memory
-		if (lo + TILE <= c.n) {
+		if (window(lo, cur.end)) {
 			mbar_wait(bar, parity);
 			parity ^= 1u;
 		} else {
-			// the window crosses the end of the array (last tile only): plain loads
+			// the window would cross the end of the array (last tile only): plain loads
 			const uint64_t *src_keys = src_b ? c.keys[1] : c.keys[0];
 			const uint64_t *src_rids = src_b ? c.rids[1] : c.rids[0];
 			for (uint32_t i = tid; i < TILE; i += THREADS) {
