@@ -99,21 +99,6 @@ __device__ __forceinline__ void emit_segment(const Ctx &c, Control *ctl, Seg *se
 	for (uint32_t j = lane; j < nt; j += 32) tiles_out[tile_at + j] = Tile{child, j};
 }
 
-// One lane: file a unit for the local sort -- packed path from the front of the array,
-// general path from the back.
-__device__ __forceinline__ void emit_unit(const Ctx &c, Control *ctl, uint32_t begin, uint32_t size,
-					  uint32_t buf, uint32_t origin)
-{
-	const bool fast = unit_packable(origin);
-	const uint32_t at = atomicAdd(fast ? &ctl->nunits : &ctl->nslow, 1u);
-	// the two lists grow towards each other; max_units bounds their sum (copy_kernel checks it)
-	if (at >= c.max_units) {
-		atomicOr(&ctl->error, 4u);
-		return;
-	}
-	c.units[fast ? at : c.max_units - 1 - at] = Unit{begin, size, buf, origin};
-}
-
 // Whole warp: final data of [begin, begin+size) sits in B, schedule its copy to A.
 __device__ __forceinline__ void emit_copy(const Ctx &c, Control *ctl, uint32_t begin, uint32_t size)
 {
@@ -208,6 +193,29 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 		// pass 2: cursors, children
 		uint32_t base = s.begin;
 		uint32_t run_beg = 0, run_size = 0, run_dig = 0, local_pairs = 0;   // warp-uniform merge state
+		// units are collected one per lane and filed 32 at a time with a single atomic
+		uint32_t nu = 0, ub = 0, us = 0, uo = 0;
+		auto file_units = [&]() {
+			if (!nu) return;
+			const bool fast = unit_packable(unit_origin(shift, 0u, bits, level == 0));
+			uint32_t at = 0;
+			if (lane == 0) {
+				at = atomicAdd(fast ? &ctl->nunits : &ctl->nslow, nu);
+				if (at + nu > c.max_units) atomicOr(&ctl->error, 4u);
+			}
+			at = __shfl_sync(0xffffffffu, at, 0);
+			if (at + nu <= c.max_units && lane < nu)
+				c.units[fast ? at + lane : c.max_units - 1 - (at + lane)] = Unit{ub, us, dst_buf, uo};
+			nu = 0;
+		};
+		auto add_unit = [&](uint32_t ubeg, uint32_t usize, uint32_t udig) {
+			if (lane == nu) {
+				ub = ubeg;
+				us = usize;
+				uo = unit_origin(shift, udig, bits, level == 0);
+			}
+			if (++nu == 32) file_units();
+		};
 		for (uint32_t b0 = 0; b0 < NB; b0 += 32) {
 			const uint32_t b = b0 + lane;
 			const uint32_t cnt = b < NB ? h[b] : 0;
@@ -217,15 +225,46 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 			base += __shfl_sync(0xffffffffu, inc, 31);
 			if (last) continue;
 
-			// buckets too large for shared memory: segments of the next level
+			// buckets too large for shared memory: segments of the next level.  One pair of
+			// atomics claims segment and tile slots for all of the chunk's children (a
+			// round trip per child made the level-0 plan, one warp, the slowest step)
 			uint32_t large = __ballot_sync(0xffffffffu, cnt > LOCAL_CAP);
-			while (large) {
-				const int src = __ffs(large) - 1;
-				large &= large - 1;
-				emit_segment(c, ctl, segs_out, tiles_out, hist_out, level, NBN,
-					     __shfl_sync(0xffffffffu, beg, src),
-					     __shfl_sync(0xffffffffu, cnt, src), dst_buf, child_shift,
-					     fused ? c.fused + size_t(b0 + src) * NBN : nullptr);
+			if (large) {
+				const bool big = cnt > LOCAL_CAP;
+				const uint32_t nt_mine = big ? seg_tile_count(beg, cnt) : 0u;
+				const uint32_t nt_inc = warp_inclusive_scan(nt_mine);
+				const uint32_t nt_all = __shfl_sync(0xffffffffu, nt_inc, 31);
+				const uint32_t nchild = __popc(large);
+				const uint32_t keys_all = __reduce_add_sync(0xffffffffu, big ? cnt : 0u);
+				uint32_t child0 = 0, tile0 = 0;
+				if (lane == 0) {
+					child0 = atomicAdd(&ctl->nsegs[level + 1], nchild);
+					tile0 = atomicAdd(&ctl->ntiles[level + 1], nt_all);
+					if (child0 + nchild > c.max_segs) atomicOr(&ctl->error, 1u);
+					if (tile0 + nt_all > c.max_tiles) atomicOr(&ctl->error, 2u);
+					if (fused) atomicAdd(&ctl->nready[level + 1], nchild);
+					else atomicAdd(&ctl->hist_keys, (unsigned long long) keys_all);
+				}
+				child0 = __shfl_sync(0xffffffffu, child0, 0);
+				tile0 = __shfl_sync(0xffffffffu, tile0, 0);
+				if (child0 + nchild <= c.max_segs && tile0 + nt_all <= c.max_tiles) {
+					const uint32_t my_child = child0 + __popc(large & ((1u << lane) - 1u));
+					const uint32_t my_tile = tile0 + nt_inc - nt_mine;
+					if (big) {
+						segs_out[my_child] = Seg{beg, cnt, dst_buf, seg_flags(child_shift, fused ? SEG_HIST_READY : 0u)};
+						((level & 1) ? c.segbits[0] : c.segbits[1])[my_child] = SegBits{0ull, ~0ull};
+					}
+					while (large) {
+						const int src = __ffs(large) - 1;
+						large &= large - 1;
+						const uint32_t child = __shfl_sync(0xffffffffu, my_child, src);
+						const uint32_t tile_at = __shfl_sync(0xffffffffu, my_tile, src);
+						const uint32_t nt = __shfl_sync(0xffffffffu, nt_mine, src);
+						const uint32_t *row = fused ? c.fused + size_t(b0 + src) * NBN : nullptr;
+						for (uint32_t j = lane; j < NBN; j += 32) hist_out[size_t(child) * NBN + j] = row ? row[j] : 0u;
+						for (uint32_t j = lane; j < nt; j += 32) tiles_out[tile_at + j] = Tile{child, j};
+					}
+				}
 			}
 			// greedy merge of neighbouring small buckets into units (all lanes in step)
 			uint32_t present = __ballot_sync(0xffffffffu, cnt != 0);
@@ -235,8 +274,7 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 				const uint32_t cb = __shfl_sync(0xffffffffu, cnt, src);
 				const uint32_t bb = __shfl_sync(0xffffffffu, beg, src);
 				if (cb > LOCAL_CAP || run_size + cb > LOCAL_CAP) {
-					if (run_size && lane == 0)
-						emit_unit(c, ctl, run_beg, run_size, dst_buf, unit_origin(shift, run_dig, bits, level == 0));
+					if (run_size) add_unit(run_beg, run_size, run_dig);
 					local_pairs += run_size;
 					run_size = 0;
 					if (cb > LOCAL_CAP) continue;
@@ -249,8 +287,8 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 			}
 		}
 		if (!last) {
-			if (run_size && lane == 0)
-				emit_unit(c, ctl, run_beg, run_size, dst_buf, unit_origin(shift, run_dig, bits, level == 0));
+			if (run_size) add_unit(run_beg, run_size, run_dig);
+			file_units();
 			local_pairs += run_size;
 			if (local_pairs && lane == 0) atomicAdd(&ctl->local_pairs, local_pairs);
 		} else if (dst_buf == 1u) {
