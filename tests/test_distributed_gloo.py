@@ -161,3 +161,36 @@ def test_choose_ranges_properties():
         c = exchange_counts(hs, t, world)
         assert np.array_equal(c.sum(axis=1), hs.sum(axis=1))
     assert np.all(choose_ranges(np.zeros(16, np.uint64), 4) == 0)
+
+
+def test_choose_ranges_hypothesis():
+    """Property test of the range cut (host logic, no process group): monotone table, every
+    destination index valid, conservation of counts, and balance within the weight of the
+    two heaviest bins (bins are never split, so that is the best any cut can promise)."""
+    from hypothesis import given, settings, strategies as st
+    from inplacemsdradixsort_b200.distributed import choose_ranges, exchange_counts
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 64), st.lists(st.integers(0, 1 << 40), min_size=1, max_size=300),
+           st.integers(0, 2 ** 32 - 1))
+    def check(world, weights, seed):
+        h = np.array(weights, dtype=np.uint64)
+        t = choose_ranges(h, world)
+        assert t.shape == h.shape and t.dtype == np.uint8
+        assert np.all(np.diff(t.astype(np.int64)) >= 0)
+        assert int(t.max()) <= world - 1
+        per = np.bincount(t, weights=h.astype(np.float64), minlength=world)
+        assert per.sum() == float(h.astype(np.float64).sum())
+        total = float(h.astype(np.float64).sum())
+        if total > 0 and world > 1:
+            top2 = float(np.sort(h.astype(np.float64))[-2:].sum())
+            assert per.max() <= total / world + top2 + 1e-6 * total
+        rng = np.random.default_rng(seed)
+        hs = rng.integers(0, 1000, size=(world, h.size)).astype(np.int64)
+        c = exchange_counts(hs, t, world)
+        assert c.shape == (world, world)
+        assert np.array_equal(c.sum(axis=1), hs.sum(axis=1))
+        for d in range(world):
+            assert int(c[:, d].sum()) == int(hs[:, t == d].sum())
+
+    check()
