@@ -23,10 +23,16 @@
 
 namespace msb64 {
 
-constexpr int LOCAL_ITEMS = 8;
+#ifndef MSB64_LOCAL_ITEMS
+#define MSB64_LOCAL_ITEMS 8
+#endif
+constexpr int LOCAL_ITEMS = MSB64_LOCAL_ITEMS;   // pairs per thread
 constexpr int LOCAL_THREADS = LOCAL_CAP / LOCAL_ITEMS;
 #ifndef MSB64_LOCAL_MINB
 #define MSB64_LOCAL_MINB 2
+#endif
+#ifndef MSB64_LOCAL_GENERAL_MINB
+#define MSB64_LOCAL_GENERAL_MINB MSB64_LOCAL_MINB
 #endif
 constexpr int LOCAL_MINB = MSB64_LOCAL_MINB;     // resident blocks per SM the register budget is cut for
 constexpr int LOCAL_OWNERS = LOCAL_THREADS >= 512 ? 512 : 256;   // threads that own bins in the scan
@@ -75,7 +81,7 @@ __device__ __forceinline__ void block_bitonic(uint64_t *k, uint64_t *r, const ui
 	}
 }
 
-__global__ void __launch_bounds__(LOCAL_THREADS, LOCAL_MINB)
+__global__ void __launch_bounds__(LOCAL_THREADS, MSB64_LOCAL_GENERAL_MINB)
 local_sort_kernel(const Ctx c, const uint64_t base_key)
 {
 	constexpr int THREADS = LOCAL_THREADS, ITEMS = LOCAL_ITEMS, WARPS = THREADS / 32;
