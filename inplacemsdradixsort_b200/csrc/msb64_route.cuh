@@ -42,11 +42,23 @@ digit_histogram_kernel(const uint64_t *keys, uint64_t n, int shift, int bits, ui
 	__syncthreads();
 	// 32-bit block counters: a block never sees more than 2^32 keys (n <= MSB64_MAX_PAIRS)
 	unsigned long long kmin = ~0ull, kmax = 0;
-	for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-		const uint64_t k = ld_stream_u64(keys + i);
-		kmin = k < kmin ? k : kmin;
-		kmax = k > kmax ? k : kmax;
-		atomicAdd(&sh[(uint32_t(k >> shift) - origin) & (nb - 1)], 1u);
+	// four independent loads per thread and trip: enough bytes in flight to fill HBM
+	for (uint64_t i = lo + threadIdx.x; i < hi; i += 4ull * blockDim.x) {
+		uint64_t k[4];
+		bool ok[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const uint64_t at = i + uint64_t(u) * blockDim.x;
+			ok[u] = at < hi;
+			k[u] = ok[u] ? ld_stream_u64(keys + at) : 0;
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+			if (ok[u]) {
+				kmin = k[u] < kmin ? k[u] : kmin;
+				kmax = k[u] > kmax ? k[u] : kmax;
+				atomicAdd(&sh[(uint32_t(k[u] >> shift) - origin) & (nb - 1)], 1u);
+			}
 	}
 	__syncthreads();
 	for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x)
