@@ -124,9 +124,11 @@ int msb64_b200_get_schedule(uint64_t n, int *bits);
 int msb64_b200_set_schedule(const int *bits, int count);
 /* The schedule msb64_b200_sort_device_range uses for keys in [key_lo, key_hi]: digit widths
  * in bits[] (returns their number), position of the first digit in *shift0 and its origin
- * (key_lo >> shift0) in *origin0: first digit = (key >> shift0) - origin0, the digits below
- * are plain bit fields under shift0 (the last one may reach below bit 0's worth of key bits:
- * its surplus high bits are bits the level above already consumed).  Needs no device. */
+ * (key_lo >> shift0) in *origin0: first digit = (key >> shift0) - origin0; the digits below
+ * are bit fields whose widths follow bits[] and whose positions start right under shift0
+ * (on the device a segment whose keys agree on more bits is moved further down, see
+ * DESIGN.md; the last digit may be wider than the key bits left: its surplus high bits were
+ * consumed by the level above).  Needs no device. */
 int msb64_b200_get_range_schedule(uint64_t n, uint64_t key_lo, uint64_t key_hi, int *bits,
 				  int *shift0, uint64_t *origin0);
 

@@ -6,8 +6,10 @@
 //
 //   init                               control block, level-0 segment / tiles
 //   for each digit (level) of the schedule:
-//       histogram -> plan -> scatter   (kernels return at once when the level is empty)
-//   local_sort                         all small-bucket units of all levels
+//       histogram -> plan -> scatter   (kernels return at once when the level is empty; the
+//                                       schedule fixes the digit WIDTH of a level, the digit's
+//                                       position travels with every segment, msb64_plan.cuh)
+//   local_sort (packed, general)       all small-bucket units of all levels
 //   copy                               finished buckets that ended in the scratch buffer
 //
 // Reference map: sort() msb_64.c:2261-2430, local_radixsort msb_64.c:1007-1035,
