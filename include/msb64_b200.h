@@ -142,6 +142,11 @@ uint64_t msb64_b200_launch_count(void);
  * Returns the number of values written. */
 int msb64_b200_last_stats(uint64_t *out, int cap);
 
+/* The device sorts are asynchronous: a work-list overflow inside one (MSB64_ERR_INTERNAL, a
+ * bug) is recorded in a page-locked status word and reported by the next call that uses the
+ * device -- or by this function, which synchronises `stream` first and clears the status. */
+int msb64_b200_last_status(void *stream);
+
 /* Per-level device times of the last msb64_b200_sort_device call that passed
  * phase_us: out[3*l + 0..2] = histogram, plan, scatter microseconds of level l.
  * Returns the number of values written (3 * levels). */
@@ -224,6 +229,67 @@ int msb64_b200_route_peer(const uint64_t *d_keys, const uint64_t *d_rids, uint64
 int msb64_b200_ipc_export(void *d_ptr, void *handle64);
 void *msb64_b200_ipc_open(const void *handle64);
 int msb64_b200_ipc_close(void *mapped);
+
+/* ------------------------------------- 5. the sort sharded over several GPUs
+ *
+ * One msb64_b200_shard per GPU: one process per GPU (the handles travel between the processes
+ * as CUDA IPC handles; inplacemsdradixsort_b200/distributed.py drives this under
+ * torch.distributed) or all of them in one process -- which is what sort() above does when it
+ * is given numa >= 2 arrays and at least as many devices are visible: node n's pairs are sorted
+ * on GPU n and node n gets the n-th key range back, the reference's contract across NUMA nodes
+ * (msb_64.c:2261-2275, 1596-1606, 2180).  MSB64_B200_SINGLE_DEVICE=1 keeps sort() on one GPU,
+ * MSB64_B200_VIRTUAL_SHARDS=1 lets the nodes share the visible devices (node n on device
+ * n mod count).
+ *
+ * A step (details in csrc/msb64_shard.cuh):
+ *   msb64_b200_shard_histogram   counts of the keys' top 12 bits + smallest / largest key into
+ *                                the shard's histogram row (msb64_b200_shard_hist: device
+ *                                pointer, msb64_b200_shard_slots() 64-bit words);
+ *   [the caller all-gathers the rows of all ranks and brings them to the host]
+ *   msb64_b200_shard_plan        host only: the same cut of the bin axis on every rank into
+ *                                world x msb64_b200_shard_subs(world) buckets of near-equal
+ *                                count; recv_caps[r] = pairs rank r can take.  Returns MSB64_OK,
+ *                                MSB64_ERR_CAPACITY (a rank would overflow; msb_64.c:1574-1578)
+ *                                or 1: the keys share a long prefix, the shard's digit was moved
+ *                                onto their real span -- histogram again (reset = 0), gather, plan;
+ *   msb64_b200_shard_exchange_sort   enqueues, without synchronising: the local bucket pass,
+ *                                the bucket-by-bucket copies into the peers' receive buffers
+ *                                over NVLink with their completion flags, and the sub-range by
+ *                                sub-range sorts of what arrives (NVLink and HBM work overlap).
+ * Afterwards msb64_b200_shard_keys / _rids hold msb64_b200_shard_count pairs: this rank's key
+ * range, ascending, every key <= every key of the next rank.  The arrays stay valid until
+ * the next step.  Between two steps every rank must have passed a collective that follows
+ * its last use of the arrays (the histogram all-gather is one).
+ * msb64_b200_shard_plan_host is the plan without a shard (no device needed). */
+typedef struct msb64_b200_shard msb64_b200_shard;
+#define MSB64_SHARD_HANDLE_BYTES 192	/* three CUDA IPC handles: receive keys, receive rids, flags */
+
+msb64_b200_shard *msb64_b200_shard_create(int rank, int world, uint64_t capacity, double fudge);
+void msb64_b200_shard_destroy(msb64_b200_shard *shard);
+int msb64_b200_shard_export(msb64_b200_shard *shard, void *handles);
+int msb64_b200_shard_connect_ipc(msb64_b200_shard *shard, const void *all_handles /* [world][192] */);
+int msb64_b200_shard_connect_local(msb64_b200_shard *const *shards, int world);
+int msb64_b200_shard_slots(void);
+int msb64_b200_shard_subs(int world);
+int msb64_b200_shard_histogram(msb64_b200_shard *shard, const uint64_t *d_keys, uint64_t n,
+			       int reset, void *stream);
+uint64_t *msb64_b200_shard_hist(msb64_b200_shard *shard);
+int msb64_b200_shard_plan(msb64_b200_shard *shard, const uint64_t *all_hists /* host [world][slots] */,
+			  const uint64_t *recv_caps /* [world] */, int may_retry);
+int msb64_b200_shard_plan_host(const uint64_t *all_hists, int world, const uint64_t *recv_caps,
+			       int may_retry, int *shift, int *bits, uint64_t *origin,
+			       uint8_t *table /* [2^bits] bin -> bucket */,
+			       uint64_t *counts /* [world][world * subs] */);
+int msb64_b200_shard_exchange_sort(msb64_b200_shard *shard, const uint64_t *d_keys,
+				   const uint64_t *d_rids, uint64_t n, void *stream, int timed);
+uint64_t msb64_b200_shard_count(const msb64_b200_shard *shard);
+uint64_t msb64_b200_shard_recv_capacity(const msb64_b200_shard *shard);
+uint64_t *msb64_b200_shard_keys(msb64_b200_shard *shard);
+uint64_t *msb64_b200_shard_rids(msb64_b200_shard *shard);
+int msb64_b200_shard_key_range(const msb64_b200_shard *shard, uint64_t *key_lo, uint64_t *key_hi);
+/* ms[0..5): route pass, wait for the first sub-range, sorting, exchange, whole step (device
+ * times of the last step run with timed = 1; synchronise the stream first). */
+int msb64_b200_shard_times(msb64_b200_shard *shard, double *ms);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,9 @@
 // schedule_passes msb_64.c:1334-1400, check() msb_64.c:2432-2505.
 #include "../../include/msb64_b200.h"
 
+#include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -143,18 +145,30 @@ RangePlan plan_range(uint64_t n, uint64_t lo, uint64_t hi)
 }
 
 // ------------------------------------------------------------------ device state
+// One record per CUDA device: kernel attributes, occupancy and cached allocations belong to
+// the device that was current when they were made, so a process that drives several GPUs
+// (the multi-device sort(), msb64_shard.cuh) gets one of each per device.
+constexpr int MAX_DEVICES = 64;
 struct Device {
 	bool ready = false;
+	int index = -1;
 	int sms = 0;
 	int hist_blocks[MAX_BITS + 1] = {0};      // resident blocks per SM, by digit width
 	int fused_blocks[MAX_BITS + 1] = {0};     // same for the fused (two-level) histogram
 	int scatter_blocks[MAX_BITS + 1] = {0};
 	int local_blocks = 0, packed_blocks = 0;
+	bool route_configured = false;
 	// cached allocations (grow-only)
 	void *ws = nullptr;
 	size_t ws_bytes = 0;
 	uint64_t *dkeys = nullptr, *drids = nullptr;
 	size_t dcap = 0;
+	unsigned long long *scratch = nullptr;    // 128 words: sort()'s node boundaries [0, 64), check() sums [64, 67)
+	// Sticky status of asynchronous sorts: the last kernel of a sort copies a non-zero
+	// Control.error into this page-locked word, the host looks at it when the device is used
+	// next (and in msb64_b200_last_status), so an untimed msb64_b200_sort_device whose work lists
+	// overflowed cannot pass unnoticed.
+	uint32_t *status_h = nullptr, *status_d = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[4 * MAX_LEVELS + 16];
 	bool events = false;
@@ -163,10 +177,10 @@ struct Device {
 	int last_levels = 0;
 	Control *last_ctl = nullptr;
 	cudaStream_t last_stream = nullptr;
-} g_dev;
+} g_devs[MAX_DEVICES];
 
 template <int BITS>
-int setup_bits()
+int setup_bits(Device &D)
 {
 	using H = HistCfg<BITS, 256>;
 	using S = ScatterCfg<BITS, SCATTER_THREADS>;
@@ -177,23 +191,23 @@ int setup_bits()
 					      cudaFuncAttributeMaxDynamicSharedMemorySize,
 					      int(H::SMEM + (size_t(H::NB + 32) << (FUSE_MAX_BITS - BITS)) * 4)));
 		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-			&g_dev.fused_blocks[BITS], histogram_kernel<BITS, 256, true>, 256,
+			&D.fused_blocks[BITS], histogram_kernel<BITS, 256, true>, 256,
 			H::SMEM + (size_t(H::NB + 32) << (FUSE_MAX_BITS - BITS)) * 4));
 	}
 	CUDA_TRY(cudaFuncSetAttribute(scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB>,
 				      cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::SMEM)));
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-		&g_dev.hist_blocks[BITS], histogram_kernel<BITS, 256, false>, 256, H::SMEM));
+		&D.hist_blocks[BITS], histogram_kernel<BITS, 256, false>, 256, H::SMEM));
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-		&g_dev.scatter_blocks[BITS], scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB>, SCATTER_THREADS, S::SMEM));
-	if (g_dev.hist_blocks[BITS] < 1 || g_dev.scatter_blocks[BITS] < 1)
+		&D.scatter_blocks[BITS], scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB>, SCATTER_THREADS, S::SMEM));
+	if (D.hist_blocks[BITS] < 1 || D.scatter_blocks[BITS] < 1)
 		return fail(MSB64_ERR_CUDA, "kernel does not fit on an SM%s");
 	return MSB64_OK;
 }
 
-int device_init()
+// The record of the CUDA device that is current on this thread, initialised on first use.
+int device_get(Device **out)
 {
-	if (g_dev.ready) return MSB64_OK;
 	int count = 0;
 	cudaError_t e = cudaGetDeviceCount(&count);
 	if (e != cudaSuccess || count == 0)
@@ -201,36 +215,61 @@ int device_init()
 			    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
 	int dev = 0;
 	CUDA_TRY(cudaGetDevice(&dev));
+	if (dev < 0 || dev >= MAX_DEVICES) return fail(MSB64_ERR_CUDA, "device index out of range%s");
+	Device &D = g_devs[dev];
+	*out = &D;
+	if (D.ready) return MSB64_OK;
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
 	if (prop.major < 10)
 		return fail(MSB64_ERR_CUDA, "device %s is not sm_100 class", prop.name);
-	g_dev.sms = prop.multiProcessorCount;
+	D.index = dev;
+	D.sms = prop.multiProcessorCount;
 	int rc;
-	if ((rc = setup_bits<4>()) || (rc = setup_bits<5>()) || (rc = setup_bits<6>()) ||
-	    (rc = setup_bits<7>()) || (rc = setup_bits<8>()) || (rc = setup_bits<9>()) ||
-	    (rc = setup_bits<10>()) || (rc = setup_bits<11>()))
+	if ((rc = setup_bits<4>(D)) || (rc = setup_bits<5>(D)) || (rc = setup_bits<6>(D)) ||
+	    (rc = setup_bits<7>(D)) || (rc = setup_bits<8>(D)) || (rc = setup_bits<9>(D)) ||
+	    (rc = setup_bits<10>(D)) || (rc = setup_bits<11>(D)))
 		return rc;
 	CUDA_TRY(cudaFuncSetAttribute(local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				      int(LOCAL_SMEM)));
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_dev.local_blocks, local_sort_kernel,
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.local_blocks, local_sort_kernel,
 							       LOCAL_THREADS, LOCAL_SMEM));
-	if (g_dev.local_blocks < 1) return fail(MSB64_ERR_CUDA, "local sort does not fit on an SM%s");
+	if (D.local_blocks < 1) return fail(MSB64_ERR_CUDA, "local sort does not fit on an SM%s");
 	CUDA_TRY(cudaFuncSetAttribute(local_sort_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 				      int(PACKED_SMEM)));
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_dev.packed_blocks, local_sort_packed_kernel,
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.packed_blocks, local_sort_packed_kernel,
 							       LOCAL_THREADS, PACKED_SMEM));
-	if (g_dev.packed_blocks < 1) return fail(MSB64_ERR_CUDA, "packed local sort does not fit on an SM%s");
-	CUDA_TRY(cudaStreamCreateWithFlags(&g_dev.stream, cudaStreamNonBlocking));
-	g_dev.ready = true;
+	if (D.packed_blocks < 1) return fail(MSB64_ERR_CUDA, "packed local sort does not fit on an SM%s");
+	CUDA_TRY(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaMalloc(&D.scratch, 128 * sizeof(unsigned long long)));
+	CUDA_TRY(cudaHostAlloc(&D.status_h, sizeof(uint32_t), cudaHostAllocMapped));
+	*D.status_h = 0;
+	CUDA_TRY(cudaHostGetDevicePointer(&D.status_d, D.status_h, 0));
+	D.ready = true;
 	return MSB64_OK;
 }
 
-int ensure_events()
+#define DEVICE_OR_RETURN()                          \
+	Device *dev_ = nullptr;                    \
+	{                                          \
+		const int rc_ = device_get(&dev_); \
+		if (rc_) return rc_;               \
+	}                                          \
+	Device &D = *dev_
+
+// Non-zero: an earlier asynchronous sort on this device reported an internal error (cleared).
+uint32_t take_status(Device &D)
 {
-	if (g_dev.events) return MSB64_OK;
-	for (auto &ev : g_dev.ev) CUDA_TRY(cudaEventCreate(&ev));
-	g_dev.events = true;
+	const uint32_t e = *static_cast<volatile uint32_t *>(D.status_h);
+	if (e) *static_cast<volatile uint32_t *>(D.status_h) = 0;
+	return e;
+}
+
+int ensure_events(Device &D)
+{
+	if (D.events) return MSB64_OK;
+	for (auto &ev : D.ev) CUDA_TRY(cudaEventCreate(&ev));
+	D.events = true;
 	return MSB64_OK;
 }
 
@@ -240,20 +279,23 @@ struct Layout {
 	uint32_t max_segs, max_tiles, max_units, max_copies;
 };
 
-Layout make_layout(uint64_t n, const std::vector<int> &sched)
+// Sized for the worst case over every schedule a sort of n pairs may get (full width, a key
+// range of any width, an override): the histogram rows take the widest digit any default
+// schedule uses (8 bits; MAX_BITS under an override) and the unit list the deepest recursion,
+// so that msb64_b200_workspace_bytes(n) is enough for msb64_b200_sort_device_range too.
+Layout make_layout(uint64_t n)
 {
 	Layout L;
-	int maxbits = 4;
-	for (int b : sched) maxbits = b > maxbits ? b : maxbits;
-	const uint64_t levels = sched.size();
+	const int maxbits = g_schedule_override.empty() ? 8 : MAX_BITS;
+	const uint64_t levels = MAX_LEVELS;
 	L.max_segs = uint32_t(n / LOCAL_CAP + 2);
 	L.max_tiles = uint32_t(n / TILE + 2 * uint64_t(L.max_segs) + 2);
 	L.max_units = uint32_t(2 * (n / LOCAL_CAP) + 2 * levels * L.max_segs + 16);
 	L.max_copies = uint32_t(n / COPY_TILE + L.max_segs + 2);
 	size_t at = 0;
 	auto take = [&](size_t bytes) { size_t o = at; at = align_up(at + bytes); return o; };
-	L.keys_b = take(n * 8);
-	L.rids_b = take(n * 8);
+	L.keys_b = take((n + 2) * 8);                 // + an odd first element and the bulk window's even rounding
+	L.rids_b = take((n + 2) * 8);
 	for (int i = 0; i < 2; ++i) L.segs[i] = take(size_t(L.max_segs) * sizeof(Seg));
 	for (int i = 0; i < 2; ++i) L.tiles[i] = take(size_t(L.max_tiles) * sizeof(Tile));
 	for (int i = 0; i < 2; ++i) L.hist[i] = take((size_t(L.max_segs) << maxbits) * 4);
@@ -268,8 +310,8 @@ Layout make_layout(uint64_t n, const std::vector<int> &sched)
 
 // ------------------------------------------------------------------ launches
 template <int BITS>
-void launch_level(const Ctx &c, int level, int shift0, uint32_t origin, int next_bits, cudaStream_t st,
-		  cudaEvent_t *ev)
+void launch_level(Device &D, const Ctx &c, int level, int shift0, uint32_t origin, int next_bits,
+		  cudaStream_t st, cudaEvent_t *ev)
 {
 	using H = HistCfg<BITS, 256>;
 	using S = ScatterCfg<BITS, SCATTER_THREADS>;
@@ -277,30 +319,35 @@ void launch_level(const Ctx &c, int level, int shift0, uint32_t origin, int next
 	// level 0 is one segment: its histogram pass also counts the level-1 digits per bin
 	// (32 KiB of shared counters), and level 1 needs no histogram pass
 	const bool fuse = level == 0 && next_bits > 0 && BITS + next_bits <= FUSE_MAX_BITS &&
-			  BITS < FUSE_MAX_BITS - 3 && g_dev.fused_blocks[BITS] > 0 && shift0 >= next_bits && !g_no_fuse;
+			  BITS < FUSE_MAX_BITS - 3 && D.fused_blocks[BITS] > 0 && shift0 >= next_bits && !g_no_fuse;
 	if (fuse) {
 		const size_t smem = H::SMEM + (size_t(H::NB + 32) << next_bits) * 4;
-		histogram_kernel<BITS, 256, true><<<g_dev.sms * g_dev.fused_blocks[BITS], 256, smem, st>>>(
+		histogram_kernel<BITS, 256, true><<<D.sms * D.fused_blocks[BITS], 256, smem, st>>>(
 			c, level, origin, next_bits);
 	} else {
-		histogram_kernel<BITS, 256, false><<<g_dev.sms * g_dev.hist_blocks[BITS], 256, H::SMEM, st>>>(
+		histogram_kernel<BITS, 256, false><<<D.sms * D.hist_blocks[BITS], 256, H::SMEM, st>>>(
 			c, level, origin, 0);
 	}
 	if (ev) cudaEventRecord(ev[1], st);
-	plan_kernel<<<g_dev.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits, fuse);
+	plan_kernel<<<D.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits, fuse);
 	if (ev) cudaEventRecord(ev[2], st);
-	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<g_dev.sms * g_dev.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, origin);
+	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<D.sms * D.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, origin);
 	if (ev) cudaEventRecord(ev[3], st);
 	g_launches += 3;
 }
 
 int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *workspace,
 		       size_t workspace_bytes, cudaStream_t st, uint64_t *phase_us,
-		       uint64_t key_lo = 0, uint64_t key_hi = ~0ull)
+		       uint64_t key_lo = 0, uint64_t key_hi = ~0ull, uint64_t begin = 0)
 {
-	int rc = device_init();
+	Device *dev = nullptr;
+	int rc = device_get(&dev);
 	if (rc) return rc;
-	if (n > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
+	Device &D = *dev;
+	if (take_status(D))
+		return fail(MSB64_ERR_INTERNAL, "an earlier asynchronous sort on this device overflowed its work lists%s");
+	if (n > MSB64_MAX_PAIRS || begin + n > MSB64_MAX_PAIRS)
+		return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
 	if (phase_us) memset(phase_us, 0, MSB64_PHASE_COUNT * sizeof(uint64_t));
 	if (n < 2) return MSB64_OK;
 	if (!d_keys || !d_rids || (uintptr_t(d_keys) & 15) || (uintptr_t(d_rids) & 15))
@@ -308,16 +355,16 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 
 	const RangePlan rp = plan_range(n, key_lo, key_hi);
 	const std::vector<int> &sched = rp.sched;
-	const Layout L = make_layout(n, sched);
+	const Layout L = make_layout(n);
 	if (!workspace) {
-		if (g_dev.ws_bytes < L.total) {
-			if (g_dev.ws) cudaFree(g_dev.ws);
-			g_dev.ws = nullptr;
-			g_dev.ws_bytes = 0;
-			CUDA_TRY(cudaMalloc(&g_dev.ws, L.total));
-			g_dev.ws_bytes = L.total;
+		if (D.ws_bytes < L.total) {
+			if (D.ws) cudaFree(D.ws);
+			D.ws = nullptr;
+			D.ws_bytes = 0;
+			CUDA_TRY(cudaMalloc(&D.ws, L.total));
+			D.ws_bytes = L.total;
 		}
-		workspace = g_dev.ws;
+		workspace = D.ws;
 	} else if (workspace_bytes < L.total || (uintptr_t(workspace) & 255)) {
 		return fail(MSB64_ERR_NOMEM, "workspace too small or not 256-byte aligned%s");
 	}
@@ -325,8 +372,10 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	Ctx c;
 	c.keys[0] = d_keys;
 	c.rids[0] = d_rids;
-	c.keys[1] = reinterpret_cast<uint64_t *>(w + L.keys_b);
-	c.rids[1] = reinterpret_cast<uint64_t *>(w + L.rids_b);
+	// the scratch copy holds elements [begin & ~1, begin + n) only: its base is shifted so that
+	// both buffers are indexed by the same element numbers
+	c.keys[1] = reinterpret_cast<uint64_t *>(w + L.keys_b) - (begin & ~1ull);
+	c.rids[1] = reinterpret_cast<uint64_t *>(w + L.rids_b) - (begin & ~1ull);
 	for (int i = 0; i < 2; ++i) {
 		c.segs[i] = reinterpret_cast<Seg *>(w + L.segs[i]);
 		c.tiles[i] = reinterpret_cast<Tile *>(w + L.tiles[i]);
@@ -337,7 +386,10 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	c.copies = reinterpret_cast<CopyTile *>(w + L.copies);
 	c.ctl = reinterpret_cast<Control *>(w + L.ctl);
 	c.fused = reinterpret_cast<uint32_t *>(w + L.fused);
+	c.status = D.status_d;
+	c.begin = uint32_t(begin);
 	c.n = uint32_t(n);
+	c.end = uint32_t(begin + n);
 	c.max_segs = L.max_segs;
 	c.max_tiles = L.max_tiles;
 	c.max_units = L.max_units;
@@ -345,12 +397,12 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 
 	cudaEvent_t *ev = nullptr;
 	if (phase_us) {
-		if ((rc = ensure_events())) return rc;
-		ev = g_dev.ev;
+		if ((rc = ensure_events(D))) return rc;
+		ev = D.ev;
 	}
 	const int levels = int(sched.size());
 	if (ev) cudaEventRecord(ev[0], st);
-	init_kernel<<<g_dev.sms, 256, 0, st>>>(c, sched[0], rp.shift0);
+	init_kernel<<<D.sms, 256, 0, st>>>(c, sched[0], rp.shift0);
 	g_launches += 1;
 	if (n > LOCAL_CAP) {
 		// the position of a segment's digit travels with the segment (msb64_plan.cuh); the
@@ -362,14 +414,14 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 			const int next_bits = l + 1 < levels ? sched[l + 1] : 0;
 			cudaEvent_t *lev = ev ? ev + 1 + 4 * l : nullptr;
 			switch (bits) {
-			case 4: launch_level<4>(c, l, shift, origin, next_bits, st, lev); break;
-			case 5: launch_level<5>(c, l, shift, origin, next_bits, st, lev); break;
-			case 6: launch_level<6>(c, l, shift, origin, next_bits, st, lev); break;
-			case 7: launch_level<7>(c, l, shift, origin, next_bits, st, lev); break;
-			case 8: launch_level<8>(c, l, shift, origin, next_bits, st, lev); break;
-			case 9: launch_level<9>(c, l, shift, origin, next_bits, st, lev); break;
-			case 10: launch_level<10>(c, l, shift, origin, next_bits, st, lev); break;
-			case 11: launch_level<11>(c, l, shift, origin, next_bits, st, lev); break;
+			case 4: launch_level<4>(D, c, l, shift, origin, next_bits, st, lev); break;
+			case 5: launch_level<5>(D, c, l, shift, origin, next_bits, st, lev); break;
+			case 6: launch_level<6>(D, c, l, shift, origin, next_bits, st, lev); break;
+			case 7: launch_level<7>(D, c, l, shift, origin, next_bits, st, lev); break;
+			case 8: launch_level<8>(D, c, l, shift, origin, next_bits, st, lev); break;
+			case 9: launch_level<9>(D, c, l, shift, origin, next_bits, st, lev); break;
+			case 10: launch_level<10>(D, c, l, shift, origin, next_bits, st, lev); break;
+			case 11: launch_level<11>(D, c, l, shift, origin, next_bits, st, lev); break;
 			default: return fail(MSB64_ERR_ARG, "digit width outside 4..11%s");
 			}
 		}
@@ -378,18 +430,18 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	if (tail) cudaEventRecord(tail[0], st);
 	// units whose keys leave room for a slot number in one word take the packed path, the rest
 	// (small arrays, very deep levels never) the general one; an empty list costs a launch
-	local_sort_packed_kernel<<<g_dev.sms * g_dev.packed_blocks, LOCAL_THREADS, PACKED_SMEM, st>>>(
+	local_sort_packed_kernel<<<D.sms * D.packed_blocks, LOCAL_THREADS, PACKED_SMEM, st>>>(
 		c, rp.origin0 << rp.shift0);
-	local_sort_kernel<<<g_dev.sms * g_dev.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(
+	local_sort_kernel<<<D.sms * D.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(
 		c, rp.origin0 << rp.shift0);
 	g_launches += 1;
 	if (tail) cudaEventRecord(tail[1], st);
-	copy_kernel<<<g_dev.sms * 8, 256, 0, st>>>(c);
+	copy_kernel<<<D.sms * 8, 256, 0, st>>>(c);
 	if (tail) cudaEventRecord(tail[2], st);
 	g_launches += 2;
 	CUDA_TRY(cudaGetLastError());
-	g_dev.last_ctl = c.ctl;
-	g_dev.last_stream = st;
+	D.last_ctl = c.ctl;
+	D.last_stream = st;
 
 	if (phase_us) {
 		CUDA_TRY(cudaStreamSynchronize(st));
@@ -402,19 +454,17 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 		if (n > LOCAL_CAP)
 			for (int l = 0; l < levels; ++l) {
 				cudaEvent_t *lev = ev + 1 + 4 * l;
-				g_dev.level_us[l][0] = us(lev[0], lev[1]);
-				g_dev.level_us[l][1] = us(lev[1], lev[2]);
-				g_dev.level_us[l][2] = us(lev[2], lev[3]);
-				phase_us[MSB64_PHASE_HISTOGRAM] += g_dev.level_us[l][0];
-				phase_us[MSB64_PHASE_PLAN] += g_dev.level_us[l][1];
-				phase_us[MSB64_PHASE_SCATTER] += g_dev.level_us[l][2];
+				D.level_us[l][0] = us(lev[0], lev[1]);
+				D.level_us[l][1] = us(lev[1], lev[2]);
+				D.level_us[l][2] = us(lev[2], lev[3]);
+				phase_us[MSB64_PHASE_HISTOGRAM] += D.level_us[l][0];
+				phase_us[MSB64_PHASE_PLAN] += D.level_us[l][1];
+				phase_us[MSB64_PHASE_SCATTER] += D.level_us[l][2];
 			}
-		g_dev.last_levels = n > LOCAL_CAP ? levels : 0;
+		D.last_levels = n > LOCAL_CAP ? levels : 0;
 		phase_us[MSB64_PHASE_LOCAL] = us(tail[0], tail[1]);
 		phase_us[MSB64_PHASE_COPY] = us(tail[1], tail[2]);
-		Control h;
-		CUDA_TRY(cudaMemcpy(&h, c.ctl, sizeof(h), cudaMemcpyDeviceToHost));
-		if (h.error) return fail(MSB64_ERR_INTERNAL, "device work list overflow%s");
+		if (take_status(D)) return fail(MSB64_ERR_INTERNAL, "device work list overflow%s");
 	}
 	return MSB64_OK;
 }
@@ -496,16 +546,38 @@ __global__ void boundary_kernel(const uint64_t *keys, uint64_t n, int numa, uint
 	bounds[node] = lo;
 }
 
-int ensure_device_arrays(uint64_t n)
+int ensure_device_arrays(Device &D, uint64_t n)
 {
-	if (g_dev.dcap >= n) return MSB64_OK;
-	if (g_dev.dkeys) cudaFree(g_dev.dkeys);
-	if (g_dev.drids) cudaFree(g_dev.drids);
-	g_dev.dkeys = g_dev.drids = nullptr;
-	g_dev.dcap = 0;
-	CUDA_TRY(cudaMalloc(&g_dev.dkeys, align_up(n * 8)));
-	CUDA_TRY(cudaMalloc(&g_dev.drids, align_up(n * 8)));
-	g_dev.dcap = n;
+	if (D.dcap >= n) return MSB64_OK;
+	if (D.dkeys) cudaFree(D.dkeys);
+	if (D.drids) cudaFree(D.drids);
+	D.dkeys = D.drids = nullptr;
+	D.dcap = 0;
+	CUDA_TRY(cudaMalloc(&D.dkeys, align_up(n * 8)));
+	CUDA_TRY(cudaMalloc(&D.drids, align_up(n * 8)));
+	D.dcap = n;
+	return MSB64_OK;
+}
+
+int digit_histogram_locked(const uint64_t *d_keys, uint64_t n, int shift, int bits, uint64_t origin,
+			   uint64_t *d_hist, uint64_t *d_minmax, cudaStream_t st)
+{
+	DEVICE_OR_RETURN();
+	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift >= 64 || !d_hist)
+		return fail(MSB64_ERR_ARG, "digit_histogram: bad shift/bits%s");
+	if (n > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
+	CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) << bits, st));
+	if (d_minmax) {
+		CUDA_TRY(cudaMemsetAsync(d_minmax, 0xff, sizeof(uint64_t), st));
+		CUDA_TRY(cudaMemsetAsync(d_minmax + 1, 0, sizeof(uint64_t), st));
+	}
+	if (n) {
+		digit_histogram_kernel<<<D.sms * 8, 256, sizeof(uint32_t) << bits, st>>>(
+			d_keys, n, shift, bits, uint32_t(origin), reinterpret_cast<unsigned long long *>(d_hist),
+			reinterpret_cast<unsigned long long *>(d_minmax));
+		g_launches += 1;
+	}
+	CUDA_TRY(cudaGetLastError());
 	return MSB64_OK;
 }
 
@@ -518,8 +590,10 @@ const char *kPhaseNames[] = {
 int sort_host_locked(uint64_t **keys, uint64_t **rids, uint64_t *size, int numa, double fudge,
 		     char **description, uint64_t *times)
 {
-	int rc = device_init();
+	Device *dev = nullptr;
+	int rc = device_get(&dev);
 	if (rc) return rc;
+	Device &D = *dev;
 	if (!keys || !rids || !size || numa < 1 || numa > 64 || !(fudge >= 1.0))
 		return fail(MSB64_ERR_ARG, "bad keys/rids/size/numa/fudge%s");
 	uint64_t total = 0;
@@ -532,29 +606,29 @@ int sort_host_locked(uint64_t **keys, uint64_t **rids, uint64_t *size, int numa,
 	if (total > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
 	if (description) description[0] = nullptr;
 	if (total == 0) return MSB64_OK;
-	if ((rc = ensure_device_arrays(total))) return rc;
-	if ((rc = ensure_events())) return rc;
-	cudaStream_t st = g_dev.stream;
-	cudaEvent_t *ev = g_dev.ev + (4 * MAX_LEVELS + 8);     // spare events past the per-level ones
+	if ((rc = ensure_device_arrays(D, total))) return rc;
+	if ((rc = ensure_events(D))) return rc;
+	cudaStream_t st = D.stream;
+	cudaEvent_t *ev = D.ev + (4 * MAX_LEVELS + 8);     // spare events past the per-level ones
 
 	CUDA_TRY(cudaEventRecord(ev[0], st));
 	uint64_t at = 0;
 	for (int n = 0; n < numa; ++n) {
 		if (!size[n]) continue;
-		CUDA_TRY(cudaMemcpyAsync(g_dev.dkeys + at, keys[n], size[n] * 8, cudaMemcpyHostToDevice, st));
-		CUDA_TRY(cudaMemcpyAsync(g_dev.drids + at, rids[n], size[n] * 8, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(D.dkeys + at, keys[n], size[n] * 8, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(D.drids + at, rids[n], size[n] * 8, cudaMemcpyHostToDevice, st));
 		at += size[n];
 	}
 	CUDA_TRY(cudaEventRecord(ev[1], st));
 	uint64_t phase[MSB64_PHASE_COUNT];
-	rc = sort_device_locked(g_dev.dkeys, g_dev.drids, total, nullptr, 0, st, times ? phase : nullptr);
+	rc = sort_device_locked(D.dkeys, D.drids, total, nullptr, 0, st, times ? phase : nullptr);
 	if (rc) return rc;
 
 	// node boundaries: exact quantiles, equal keys never split (msb_64.c:1596-1606)
 	std::vector<uint64_t> bounds(numa, total);
 	if (numa > 1) {
-		uint64_t *d_bounds = reinterpret_cast<uint64_t *>(g_dev.ws);   // B keys are dead now
-		boundary_kernel<<<1, 64, 0, st>>>(g_dev.dkeys, total, numa, d_bounds);
+		uint64_t *d_bounds = reinterpret_cast<uint64_t *>(D.scratch);
+		boundary_kernel<<<1, 64, 0, st>>>(D.dkeys, total, numa, d_bounds);
 		g_launches += 1;
 		CUDA_TRY(cudaMemcpyAsync(bounds.data(), d_bounds, numa * 8, cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
@@ -571,19 +645,15 @@ int sort_host_locked(uint64_t **keys, uint64_t **rids, uint64_t *size, int numa,
 	for (int n = 0; n < numa; ++n) {
 		const uint64_t cnt = bounds[n] - prev;
 		if (cnt) {
-			CUDA_TRY(cudaMemcpyAsync(keys[n], g_dev.dkeys + prev, cnt * 8, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaMemcpyAsync(rids[n], g_dev.drids + prev, cnt * 8, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(keys[n], D.dkeys + prev, cnt * 8, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(rids[n], D.drids + prev, cnt * 8, cudaMemcpyDeviceToHost, st));
 		}
 		size[n] = cnt;
 		prev = bounds[n];
 	}
 	CUDA_TRY(cudaEventRecord(ev[3], st));
 	CUDA_TRY(cudaStreamSynchronize(st));
-	if (total >= 2) {
-		Control h;
-		CUDA_TRY(cudaMemcpy(&h, g_dev.last_ctl, sizeof(h), cudaMemcpyDeviceToHost));
-		if (h.error) return fail(MSB64_ERR_INTERNAL, "device work list overflow%s");
-	}
+	if (take_status(D)) return fail(MSB64_ERR_INTERNAL, "device work list overflow%s");
 	if (times && description) {
 		float h2d = 0, d2h = 0;
 		cudaEventElapsedTime(&h2d, ev[0], ev[1]);
@@ -599,6 +669,179 @@ int sort_host_locked(uint64_t **keys, uint64_t **rids, uint64_t *size, int numa,
 
 } // namespace
 
+#include "msb64_shard.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ sort() over several GPUs
+// numa >= 2 arrays and as many usable devices: node n's pairs go to GPU n, the GPUs run the
+// sharded sort (msb64_shard.cuh) over peer memory, and node n gets the n-th key range back --
+// the reference's own contract across NUMA nodes (msb_64.c:2261-2275, 1596-1606, 2180).
+// Host <-> device copies of the nodes run concurrently, one PCIe link each.
+// MSB64_B200_VIRTUAL_SHARDS=1 lets several shards share a device (node n on device n mod
+// count): the same code path on a box with a single GPU.
+std::vector<msb64_b200_shard *> g_host_shards;
+const char *kShardPhaseNames[] = {
+	"Copy to device time:      ", "Histogram + plan time:    ", "Route + exchange + sort:  ",
+	"Copy to host time:        ",
+};
+
+int host_shard_devices(int numa)
+{
+	int count = 0;
+	if (numa < 2 || cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return 0;
+	const char *v = getenv("MSB64_B200_VIRTUAL_SHARDS");
+	if (count >= numa) return getenv("MSB64_B200_SINGLE_DEVICE") ? 0 : numa;
+	return v && atoi(v) > 0 ? count : 0;
+}
+
+void drop_host_shards()
+{
+	for (auto *S : g_host_shards) shard_free(S);
+	g_host_shards.clear();
+}
+
+int sort_host_sharded_locked(uint64_t **keys, uint64_t **rids, uint64_t *size, int numa, double fudge,
+			     char **description, uint64_t *times, int ndev)
+{
+	using clk = std::chrono::steady_clock;
+	if (!keys || !rids || !size || numa < 2 || numa > SHARD_MAX_WORLD || !(fudge >= 1.0))
+		return fail(MSB64_ERR_ARG, "bad keys/rids/size/numa/fudge%s");
+	uint64_t total = 0;
+	for (int n = 0; n < numa; ++n) {
+		if (size[n] && (!keys[n] || !rids[n])) return fail(MSB64_ERR_ARG, "NULL array%s");
+		if ((uintptr_t(keys[n]) & 15) || (uintptr_t(rids[n]) & 15))
+			return fail(MSB64_ERR_ARG, "arrays must be 16-byte aligned (msb_64.c:2272)%s");
+		if (uint64_t(double(size[n]) * fudge) + 2 > MSB64_MAX_PAIRS)
+			return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs per GPU%s");
+		total += size[n];
+	}
+	if (description) description[0] = nullptr;
+	if (total == 0) return MSB64_OK;
+	int prev_dev = 0;
+	CUDA_TRY(cudaGetDevice(&prev_dev));
+	struct Restore {
+		int dev;
+		~Restore() { cudaSetDevice(dev); }
+	} restore{prev_dev};
+
+	// the shards of this process (kept between calls while they are large enough)
+	bool reuse = int(g_host_shards.size()) == numa;
+	for (int n = 0; reuse && n < numa; ++n) {
+		const msb64_b200_shard *S = g_host_shards[n];
+		reuse = S->device == n % ndev && S->capacity >= size[n] &&
+			S->recv_cap >= uint64_t(double(size[n]) * fudge);
+	}
+	if (!reuse) {
+		drop_host_shards();
+		for (int n = 0; n < numa; ++n) {
+			CUDA_TRY(cudaSetDevice(n % ndev));
+			msb64_b200_shard *S = shard_create_locked(n, numa, size[n], fudge);
+			if (!S) {
+				drop_host_shards();
+				return MSB64_ERR_NOMEM;
+			}
+			g_host_shards.push_back(S);
+			if (cudaMalloc(&S->in_keys, (S->capacity + 2) * 8) != cudaSuccess ||
+			    cudaMalloc(&S->in_rids, (S->capacity + 2) * 8) != cudaSuccess ||
+			    cudaHostAlloc(&S->h_hist, SHARD_SLOTS * 8, cudaHostAllocDefault) != cudaSuccess ||
+			    cudaStreamCreateWithFlags(&S->main, cudaStreamNonBlocking) != cudaSuccess) {
+				snprintf(g_err, sizeof(g_err), "sort(): device memory for node %d: %s", n,
+					 cudaGetErrorString(cudaGetLastError()));
+				drop_host_shards();
+				return MSB64_ERR_NOMEM;
+			}
+		}
+		const int rc = shard_connect_local_locked(g_host_shards.data(), numa);
+		if (rc) {
+			drop_host_shards();
+			return rc;
+		}
+	}
+	auto &sh = g_host_shards;
+	auto sync_all = [&]() -> int {
+		for (int n = 0; n < numa; ++n) {
+			CUDA_TRY(cudaSetDevice(sh[n]->device));
+			CUDA_TRY(cudaStreamSynchronize(sh[n]->main));
+		}
+		return MSB64_OK;
+	};
+	int rc;
+	const auto t0 = clk::now();
+	for (int n = 0; n < numa; ++n) {
+		CUDA_TRY(cudaSetDevice(sh[n]->device));
+		if (!size[n]) continue;
+		CUDA_TRY(cudaMemcpyAsync(sh[n]->in_keys, keys[n], size[n] * 8, cudaMemcpyHostToDevice, sh[n]->main));
+		CUDA_TRY(cudaMemcpyAsync(sh[n]->in_rids, rids[n], size[n] * 8, cudaMemcpyHostToDevice, sh[n]->main));
+	}
+	if ((rc = sync_all())) return rc;
+	const auto t1 = clk::now();
+
+	// steps 1-3: histograms, "all-gather" through page-locked host memory, the plan
+	std::vector<uint64_t> hists(size_t(numa) * SHARD_SLOTS), caps(numa);
+	for (int n = 0; n < numa; ++n) caps[n] = std::min(sh[n]->recv_cap, uint64_t(double(size[n]) * fudge));   // msb_64.c:1574
+	for (int round = 0;; ++round) {
+		for (int n = 0; n < numa; ++n) {
+			if (round) sh[n]->plan = sh[0]->plan;            // the window every shard histograms on
+			if ((rc = shard_histogram_locked(*sh[n], sh[n]->in_keys, size[n], round == 0, sh[n]->main))) return rc;
+			DeviceGuard guard(sh[n]->device);
+			CUDA_TRY(cudaMemcpyAsync(sh[n]->h_hist, sh[n]->d_hist, SHARD_SLOTS * 8, cudaMemcpyDeviceToHost, sh[n]->main));
+		}
+		if ((rc = sync_all())) return rc;
+		for (int n = 0; n < numa; ++n) memcpy(&hists[size_t(n) * SHARD_SLOTS], sh[n]->h_hist, SHARD_SLOTS * 8);
+		rc = shard_plan(sh[0]->plan, hists.data(), numa, caps.data(), round == 0);
+		if (rc == 1 && round == 0) continue;
+		if (rc) return rc;
+		for (int n = 1; n < numa; ++n) sh[n]->plan = sh[0]->plan;
+		break;
+	}
+	const auto t2 = clk::now();
+
+	// steps 4-6, interleaved over the shards: nothing a shard waits for is enqueued after the wait
+	for (int n = 0; n < numa; ++n) {
+		sh[n]->timed = false;
+		if ((rc = shard_prepare_locked(*sh[n], sh[n]->in_keys, sh[n]->in_rids, size[n]))) return rc;
+	}
+	for (int n = 0; n < numa; ++n)
+		if ((rc = shard_route_exchange_locked(*sh[n], sh[n]->in_keys, sh[n]->in_rids, size[n], sh[n]->main))) return rc;
+	for (int n = 0; n < numa; ++n)
+		if ((rc = shard_wait_sort_locked(*sh[n], sh[n]->main))) return rc;
+	if ((rc = sync_all())) return rc;
+	const auto t3 = clk::now();
+
+	for (int n = 0; n < numa; ++n) {
+		CUDA_TRY(cudaSetDevice(sh[n]->device));
+		const uint64_t cnt = sh[n]->recv_total;
+		if (cnt) {
+			CUDA_TRY(cudaMemcpyAsync(keys[n], sh[n]->recv_keys, cnt * 8, cudaMemcpyDeviceToHost, sh[n]->main));
+			CUDA_TRY(cudaMemcpyAsync(rids[n], sh[n]->recv_rids, cnt * 8, cudaMemcpyDeviceToHost, sh[n]->main));
+		}
+		size[n] = cnt;
+	}
+	if ((rc = sync_all())) return rc;
+	const auto t4 = clk::now();
+	for (int n = 0; n < numa; ++n) {
+		Device *dev = nullptr;
+		CUDA_TRY(cudaSetDevice(sh[n]->device));
+		if ((rc = device_get(&dev))) return rc;
+		if (take_status(*dev)) return fail(MSB64_ERR_INTERNAL, "device work list overflow%s");
+	}
+	if (times && description) {
+		auto us = [](clk::time_point a, clk::time_point b) {
+			return uint64_t(std::chrono::duration_cast<std::chrono::microseconds>(b - a).count());
+		};
+		times[0] = us(t0, t1);
+		times[1] = us(t1, t2);
+		times[2] = us(t2, t3);
+		times[3] = us(t3, t4);
+		for (int p = 0; p < 4; ++p) description[p] = const_cast<char *>(kShardPhaseNames[p]);
+		description[4] = nullptr;
+	}
+	return MSB64_OK;
+}
+
+} // namespace
+
 // =================================================================== C ABI
 extern "C" {
 
@@ -607,6 +850,8 @@ int msb64_b200_sort(uint64_t **keys, uint64_t **rids, uint64_t *size, int thread
 {
 	(void) threads;
 	std::lock_guard<std::mutex> lock(g_mutex);
+	const int ndev = host_shard_devices(numa);
+	if (ndev > 0) return sort_host_sharded_locked(keys, rids, size, numa, fudge, description, times, ndev);
 	return sort_host_locked(keys, rids, size, numa, fudge, description, times);
 }
 
@@ -635,7 +880,7 @@ int msb64_b200_sort_host(uint64_t *keys, uint64_t *rids, uint64_t n)
 size_t msb64_b200_workspace_bytes(uint64_t n)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
-	return make_layout(n, make_schedule(n)).total;
+	return make_layout(n).total;
 }
 
 int msb64_b200_sort_device(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *workspace,
@@ -707,10 +952,13 @@ uint64_t msb64_b200_launch_count(void) { return g_launches.load(); }
 int msb64_b200_last_stats(uint64_t *out, int cap)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
-	if (!g_dev.last_ctl) return 0;
-	if (cudaStreamSynchronize(g_dev.last_stream) != cudaSuccess) return 0;
+	Device *dev = nullptr;
+	if (device_get(&dev)) return 0;
+	Device &D = *dev;
+	if (!D.last_ctl) return 0;
+	if (cudaStreamSynchronize(D.last_stream) != cudaSuccess) return 0;
 	Control h;
-	if (cudaMemcpy(&h, g_dev.last_ctl, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+	if (cudaMemcpy(&h, D.last_ctl, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
 	int k = 0;
 	for (int l = 0; l < MAX_LEVELS && k < cap; ++l) out[k++] = h.nsegs[l];
 	for (int l = 0; l < MAX_LEVELS && k < cap; ++l) out[k++] = h.ntiles[l];
@@ -727,9 +975,12 @@ int msb64_b200_last_stats(uint64_t *out, int cap)
 int msb64_b200_last_level_times(uint64_t *out, int cap)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
+	Device *dev = nullptr;
+	if (device_get(&dev)) return 0;
+	Device &D = *dev;
 	int k = 0;
-	for (int l = 0; l < g_dev.last_levels; ++l)
-		for (int j = 0; j < 3 && k < cap; ++j) out[k++] = g_dev.level_us[l][j];
+	for (int l = 0; l < D.last_levels; ++l)
+		for (int j = 0; j < 3 && k < cap; ++j) out[k++] = D.level_us[l][j];
 	return k;
 }
 
@@ -737,52 +988,32 @@ int msb64_b200_digit_histogram(const uint64_t *d_keys, uint64_t n, int shift, in
 				uint64_t *d_hist, uint64_t *d_minmax, void *stream)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
-	int rc = device_init();
-	if (rc) return rc;
-	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift >= 64 || !d_hist)
-		return fail(MSB64_ERR_ARG, "digit_histogram: bad shift/bits%s");
-	if (n > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
-	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) << bits, st));
-	if (d_minmax) {
-		CUDA_TRY(cudaMemsetAsync(d_minmax, 0xff, sizeof(uint64_t), st));
-		CUDA_TRY(cudaMemsetAsync(d_minmax + 1, 0, sizeof(uint64_t), st));
-	}
-	if (n) {
-		digit_histogram_kernel<<<g_dev.sms * 8, 256, sizeof(uint32_t) << bits, st>>>(
-			d_keys, n, shift, bits, uint32_t(origin), reinterpret_cast<unsigned long long *>(d_hist),
-			reinterpret_cast<unsigned long long *>(d_minmax));
-		g_launches += 1;
-	}
-	CUDA_TRY(cudaGetLastError());
-	return MSB64_OK;
+	return digit_histogram_locked(d_keys, n, shift, bits, origin, d_hist, d_minmax, static_cast<cudaStream_t>(stream));
 }
 
 static int route_common(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n, int shift, int bits,
 			uint64_t origin, const uint8_t *d_bin_to_dest, int ndest, uint32_t *d_cursors, const RouteDst &dst,
 			void *stream)
 {
-	int rc = device_init();
-	if (rc) return rc;
+	DEVICE_OR_RETURN();
 	if (bits < 1 || bits > ROUTE_MAX_BITS || shift < 0 || shift >= 64 || ndest < 1 ||
 	    ndest > ROUTE_MAX_DEST || !d_bin_to_dest || !d_cursors)
 		return fail(MSB64_ERR_ARG, "route: bad shift/bits/ndest%s");
 	if (n > MSB64_MAX_PAIRS) return fail(MSB64_ERR_TOO_BIG, "more than MSB64_MAX_PAIRS pairs%s");
 	if (!n) return MSB64_OK;
-	static bool configured = false;
-	if (!configured) {
+	if (!D.route_configured) {
 		CUDA_TRY(cudaFuncSetAttribute(route_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 					      int(RouteCfg<16>::SMEM)));
 		CUDA_TRY(cudaFuncSetAttribute(route_kernel<ROUTE_MAX_DEST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 					      int(RouteCfg<ROUTE_MAX_DEST>::SMEM)));
-		configured = true;
+		D.route_configured = true;
 	}
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	if (ndest <= 16)
-		route_kernel<16><<<g_dev.sms * 3, ROUTE_THREADS, RouteCfg<16>::SMEM, st>>>(
+		route_kernel<16><<<D.sms * 3, ROUTE_THREADS, RouteCfg<16>::SMEM, st>>>(
 			d_keys, d_rids, uint32_t(n), shift, bits, uint32_t(origin), d_bin_to_dest, ndest, d_cursors, dst);
 	else
-		route_kernel<ROUTE_MAX_DEST><<<g_dev.sms * 2, ROUTE_THREADS, RouteCfg<ROUTE_MAX_DEST>::SMEM, st>>>(
+		route_kernel<ROUTE_MAX_DEST><<<D.sms * 2, ROUTE_THREADS, RouteCfg<ROUTE_MAX_DEST>::SMEM, st>>>(
 			d_keys, d_rids, uint32_t(n), shift, bits, uint32_t(origin), d_bin_to_dest, ndest, d_cursors, dst);
 	g_launches += 1;
 	CUDA_TRY(cudaGetLastError());
@@ -887,10 +1118,9 @@ int msb64_b200_fill(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, int kind, ui
 		    uint64_t param, void *stream)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
-	int rc = device_init();
-	if (rc) return rc;
+	DEVICE_OR_RETURN();
 	if (!n) return MSB64_OK;
-	fill_kernel<<<g_dev.sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_keys, d_rids, n, kind,
+	fill_kernel<<<D.sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_keys, d_rids, n, kind,
 										seed, param);
 	g_launches += 1;
 	CUDA_TRY(cudaGetLastError());
@@ -901,20 +1131,25 @@ int msb64_b200_check(const uint64_t *d_keys, const uint64_t *d_rids, uint64_t n,
 		     void *stream)
 {
 	std::lock_guard<std::mutex> lock(g_mutex);
-	int rc = device_init();
-	if (rc) return rc;
+	DEVICE_OR_RETURN();
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
-	unsigned long long *d_out = nullptr;
-	CUDA_TRY(cudaMalloc(&d_out, 3 * sizeof(unsigned long long)));
+	unsigned long long *d_out = D.scratch + 64;        // the device's cached scratch words
 	CUDA_TRY(cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), st));
 	if (n) {
-		check_kernel<<<g_dev.sms * 8, 256, 0, st>>>(d_keys, d_rids, n, d_out);
+		check_kernel<<<D.sms * 8, 256, 0, st>>>(d_keys, d_rids, n, d_out);
 		g_launches += 1;
 	}
-	cudaError_t e = cudaMemcpyAsync(out, d_out, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-	cudaFree(d_out);
-	CUDA_TRY(e);
+	CUDA_TRY(cudaMemcpyAsync(out, d_out, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	return MSB64_OK;
+}
+
+int msb64_b200_last_status(void *stream)
+{
+	std::lock_guard<std::mutex> lock(g_mutex);
+	DEVICE_OR_RETURN();
+	CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+	if (take_status(D)) return fail(MSB64_ERR_INTERNAL, "device work list overflow%s");
 	return MSB64_OK;
 }
 

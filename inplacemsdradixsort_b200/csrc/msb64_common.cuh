@@ -118,7 +118,10 @@ struct Ctx {
 	CopyTile *copies;
 	Control *ctl;
 	uint32_t *fused;         // [2^bits0][2^bits1] level-1 digit counts per level-0 bin (fused histogram pass)
+	uint32_t *status;        // page-locked host word: receives a non-zero Control.error at the end of the sort
+	uint32_t begin;          // the sort's pairs are elements [begin, begin + n) of keys[] / rids[]
 	uint32_t n;
+	uint32_t end;            // begin + n: no kernel touches an element at or past it (rounded up to even)
 	uint32_t max_segs, max_tiles, max_units, max_copies;
 };
 

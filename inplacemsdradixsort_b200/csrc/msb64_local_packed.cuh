@@ -107,7 +107,7 @@ local_sort_packed_kernel(const Ctx c, const uint64_t base_key)
 		// fetch without leaving the array (block-uniform)
 		const uint32_t a = begin & 1u;
 		uint32_t elems = (a + size + 1u) & ~1u;
-		const bool tail = (begin - a) + elems > c.n;              // the window's last slot is past the array
+		const bool tail = (begin - a) + elems > c.end;             // the window's last slot is past the array
 		if (tail) elems -= 2;
 		{
 			uint4 *b4 = reinterpret_cast<uint4 *>(bins);

@@ -26,7 +26,7 @@ __global__ void init_kernel(const Ctx c, const int bits0, const int shift0)
 {
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t gsize = gridDim.x * blockDim.x;
-	const uint32_t nt = seg_tile_count(0, c.n);
+	const uint32_t nt = seg_tile_count(c.begin, c.n);
 	if (gtid == 0) {
 		Control *ctl = c.ctl;
 		for (int l = 0; l <= MAX_LEVELS; ++l) {
@@ -45,11 +45,11 @@ __global__ void init_kernel(const Ctx c, const int bits0, const int shift0)
 		if (c.n > LOCAL_CAP) {
 			ctl->nsegs[0] = 1;
 			ctl->ntiles[0] = nt;
-			c.segs[0][0] = Seg{0u, c.n, 0u, seg_flags(shift0, 0u)};
+			c.segs[0][0] = Seg{c.begin, c.n, 0u, seg_flags(shift0, 0u)};
 			c.segbits[0][0] = SegBits{0ull, ~0ull};
 		} else if (c.n > 0) {
 			ctl->nslow = 1;                                  // nothing known about the keys: general path
-			c.units[c.max_units - 1] = Unit{0u, c.n, 0u, 0u};
+			c.units[c.max_units - 1] = Unit{c.begin, c.n, 0u, 0u};
 		}
 	}
 	if (c.n > LOCAL_CAP) {
@@ -301,8 +301,15 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 __global__ void __launch_bounds__(256)
 copy_kernel(const Ctx c)
 {
-	if (blockIdx.x == 0 && threadIdx.x == 0 && c.ctl->nunits + c.ctl->nslow > c.max_units)
-		atomicOr(&c.ctl->error, 4u);                  // the two unit lists ran into each other
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		uint32_t e = c.ctl->error;
+		if (c.ctl->nunits + c.ctl->nslow > c.max_units) {     // the two unit lists ran into each other
+			e |= 4u;
+			atomicOr(&c.ctl->error, 4u);
+		}
+		// last kernel of the sort: tell the host (sticky, read at the device's next use)
+		if (e && c.status) *reinterpret_cast<volatile uint32_t *>(c.status) = e;
+	}
 	const uint32_t ncopies = min(c.ctl->ncopies, c.max_copies);
 	for (uint32_t t = blockIdx.x; t < ncopies; t += gridDim.x) {
 		const CopyTile ct = c.copies[t];

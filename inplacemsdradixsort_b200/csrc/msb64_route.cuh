@@ -87,7 +87,9 @@ constexpr uint32_t ROUTE_ALIGN = 16;     // pairs: every destination's run is wr
 
 template <int ND>
 struct RouteCfg {
-	static constexpr uint32_t SLOTS = TILE + ROUTE_ALIGN * ND;              // padded destination-ordered positions
+	// padded destination-ordered positions: every non-empty destination adds up to ROUTE_ALIGN - 1
+	// slots in front of its run and as many behind it
+	static constexpr uint32_t SLOTS = TILE + 2 * ROUTE_ALIGN * ND;
 	static constexpr size_t SMEM = size_t(TILE) * 16                        // keys + rids of the tile (bulk-copied)
 				       + size_t(SLOTS) * 2                      // source slot by padded position
 				       + (ND + 32) * 4                          // per-destination counters (+ dummies)
@@ -222,10 +224,169 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 				st_stream_u64(orids[d] + at, rid);
 			}
 		}
+		__syncthreads();                                      // every thread is done with sidx / delta / the tile
 		for (uint32_t i = tid; i < ND + 32; i += THREADS) cnt[i] = 0;
-		__syncthreads();
 		if (tid == 0) start_copy(t + gridDim.x);
+		__syncthreads();
 	}
+}
+
+
+// ---------------------------------------------------------------------------------------
+// bucket_route_kernel -- first pass of the pipelined multi-GPU sort (msb64_shard.cuh): the
+// rank's pairs are grouped by BUCKET = table[digit], where a bucket is one (destination GPU,
+// sub-range) cell of the range partition: destination d owns buckets [d * subs, (d + 1) * subs)
+// and inside a destination the sub-ranges are ascending key ranges of near-equal count.  It is
+// an MSD partition pass on splitters instead of a bit field (the reference partitions on
+// sampled delimiters the same way, msb_64.c:497-699), written locally at HBM speed: the
+// buckets of other GPUs land bucket by bucket in a staging buffer, from where whole buckets
+// travel over NVLink as large contiguous copies while the destination already sorts the
+// buckets that have arrived; the rank's own buckets go straight to their final place in its
+// receive buffer.
+//
+// Structure of scatter_kernel (msb64_scatter.cuh) on a flat array: bulk-copied tile, shared
+// atomics for the ranks, one global atomicAdd per non-empty bucket on cursors[bucket], a
+// 2-byte source-slot permutation and a coalesced write-out.  Algorithmic traffic 32 B/pair.
+struct BucketOut {
+	uint64_t *keys[2];       // [0] staging, [1] the rank's own receive buffer
+	uint64_t *rids[2];
+	uint32_t own_first;      // buckets [own_first, own_first + own_count) go to [1]
+	uint32_t own_count;
+};
+
+template <int NBK>
+struct BucketCfg {
+	static constexpr int THREADS = 256;
+	static constexpr int ITEMS = TILE / THREADS;
+	static constexpr size_t SMEM = size_t(TILE) * 16 + size_t(TILE) * 2 + size_t(NBK + 32) * 4 + size_t(NBK) * 4
+				       + 64 * 4 + 16;
+};
+
+template <int NBK>
+__global__ void __launch_bounds__(256, 3)
+bucket_route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, uint32_t tmask,
+		    uint32_t origin, const uint8_t *__restrict__ table, uint32_t *cursors, const BucketOut out)
+{
+	using Cfg = BucketCfg<NBK>;
+	constexpr int THREADS = Cfg::THREADS, ITEMS = Cfg::ITEMS;
+	static_assert(NBK <= THREADS, "one owner thread per bucket");
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint64_t *kin = reinterpret_cast<uint64_t *>(smem_raw);               // [TILE]
+	uint64_t *rin = kin + TILE;                                           // [TILE]
+	uint16_t *sidx = reinterpret_cast<uint16_t *>(rin + TILE);            // [TILE]
+	uint32_t *cnt = reinterpret_cast<uint32_t *>(sidx + TILE);            // [NBK + 32]
+	uint32_t *delta = cnt + NBK + 32;                                     // [NBK]
+	uint32_t *scratch = delta + NBK;                                      // [64]
+	uint64_t *bar = reinterpret_cast<uint64_t *>(scratch + 64);
+
+	const uint32_t tid = threadIdx.x, lane = lane_id();
+	const uint32_t ntiles = (n + TILE - 1) / TILE;
+	if (blockIdx.x >= ntiles) return;
+	auto start_copy = [&](uint32_t t) {
+		if (t >= ntiles || (t + 1) * uint64_t(TILE) > n) return;
+		mbar_expect_tx(bar, TILE * 16);
+		bulk_copy_g2s(kin, keys + size_t(t) * TILE, TILE * 8, bar);
+		bulk_copy_g2s(rin, rids + size_t(t) * TILE, TILE * 8, bar);
+	};
+	auto bucket_of = [&](uint64_t key) -> uint32_t {
+		return uint32_t(__ldg(table + ((uint32_t(key >> shift) - origin) & tmask)));
+	};
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		start_copy(blockIdx.x);
+	}
+	for (uint32_t i = tid; i < NBK + 32; i += THREADS) cnt[i] = 0;
+	__syncthreads();
+
+	uint32_t parity = 0;
+	for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		const uint32_t lo = t * TILE;
+		const uint32_t count = min(TILE, n - lo);
+		if (count == TILE) {
+			mbar_wait(bar, parity);
+			parity ^= 1u;
+		} else {
+			for (uint32_t i = tid; i < count; i += THREADS) {
+				kin[i] = ld_stream_u64(keys + lo + i);
+				rin[i] = ld_stream_u64(rids + lo + i);
+			}
+			__syncthreads();
+		}
+		uint32_t dr[ITEMS];
+		{
+			const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(kin);
+#pragma unroll
+			for (int jj = 0; jj < ITEMS / 2; ++jj) {
+				const ulonglong2 v = k2[jj * THREADS + tid];
+				const uint32_t s0 = (jj * THREADS + tid) * 2;
+				dr[2 * jj] = s0 < count ? bucket_of(v.x) : NBK + lane;
+				dr[2 * jj + 1] = s0 + 1 < count ? bucket_of(v.y) : NBK + lane;
+			}
+		}
+		tile_ranks<ITEMS, NBK>(cnt, dr);
+		__syncthreads();
+		// owner thread of every bucket: claim the tile's slice, exclusive scan over the buckets
+		const uint32_t tot = tid < NBK ? cnt[tid] : 0;
+		const uint32_t g = tot ? atomicAdd(&cursors[tid], tot) : 0;
+		uint32_t total;
+		const uint32_t lbase = block_exclusive_scan<THREADS>(tot, scratch, &total);
+		if (tid < NBK) {
+			cnt[tid] = lbase;
+			delta[tid] = g - lbase;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int j = 0; j < ITEMS; ++j) {
+			const uint32_t d = dr[j] >> RANK_BITS;
+			if (d < NBK) sidx[cnt[d] + (dr[j] & RANK_MASK)] = uint16_t(((j >> 1) * THREADS + tid) * 2 + (j & 1));
+		}
+		__syncthreads();
+#pragma unroll 8
+		for (uint32_t i = tid; i < count; i += THREADS) {
+			const uint32_t s = sidx[i];
+			const uint64_t key = kin[s];
+			const uint64_t rid = rin[s];
+			const uint32_t b = bucket_of(key);
+			const uint32_t own = (b - out.own_first) < out.own_count ? 1u : 0u;
+			const uint32_t at = delta[b] + i;
+			st_stream_u64(out.keys[own] + at, key);
+			st_stream_u64(out.rids[own] + at, rid);
+		}
+		__syncthreads();
+		for (uint32_t i = tid; i < NBK + 32; i += THREADS) cnt[i] = 0;
+		if (tid == 0) start_copy(t + gridDim.x);
+		__syncthreads();
+	}
+}
+
+// ---- completion flags of the pipelined exchange (msb64_shard.cuh)
+// signal: one thread per peer writes `epoch` into that peer's flag word for (lane, sub, this
+// source); the copies that precede it in the stream have completed, the fence orders them
+// before the flag for an observer on another GPU.
+struct FlagDst {
+	uint32_t *flag[ROUTE_MAX_DEST];
+};
+__global__ void shard_signal_kernel(const FlagDst dst, int world, int self, uint32_t slot, uint32_t epoch)
+{
+	const int d = threadIdx.x;
+	if (d >= world || d == self) return;
+	__threadfence_system();
+	*reinterpret_cast<volatile uint32_t *>(dst.flag[d] + slot) = epoch;
+}
+// wait: spins until every source's flag words of the given lanes of sub-range `sub` carry this epoch
+__global__ void shard_wait_kernel(const uint32_t *flags, int world, int self, int subs, int sub, int lanes,
+				  uint32_t epoch)
+{
+	const int t = threadIdx.x;
+	if (t < world * lanes) {
+		const int src = t % world, lane = t / world;
+		if (src != self) {
+			const volatile uint32_t *f = flags + (size_t(lane) * subs + sub) * world + src;
+			while (int32_t(*f - epoch) < 0) __nanosleep(200);
+		}
+	}
+	__syncthreads();
+	__threadfence_system();
 }
 
 } // namespace msb64

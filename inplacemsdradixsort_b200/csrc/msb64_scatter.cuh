@@ -162,7 +162,7 @@ scatter_kernel(const Ctx c, const int level, const uint32_t origin)
 	// of traffic.  0 = the window would leave the array (last tile only): plain loads instead.
 	auto window = [&](uint32_t lo, uint32_t end) -> uint32_t {
 		const uint32_t w = min(uint32_t(TILE), (end - lo + 1u) & ~1u);
-		return lo + w <= c.n ? w : 0u;
+		return lo + w <= c.end ? w : 0u;
 	};
 	// thread 0 only (slots in front of the segment receive the neighbours' data and are ignored)
 	auto start_copy = [&](const TileDesc &d) {

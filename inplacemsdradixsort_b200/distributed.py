@@ -2,42 +2,37 @@
 
 The role of the reference's cross-NUMA-node phase (sample -> range histogram ->
 partition into per-node ranges -> every thread sorts its range; msb_64.c:1546-1606,
-1674-2198), re-thought for GPUs connected by NVLink/NVSwitch:
+1674-2198), re-thought for GPUs connected by NVLink/NVSwitch.  Three forms of the exchange:
 
-    1. every rank histograms the top `bits` bits of its keys and notes its smallest and
-       largest key                                                    (device kernel)
-    2. the histograms are all-gathered                                (NCCL)
-       -- if that cut would overload a rank because the keys share a long prefix (only low
-       bits significant, a narrow value range), steps 1-2 are repeated once on a window
-       placed on the keys' real span [global min, global max] (the reference reaches the
-       same end with delimiters sampled from the data, msb_64.c:239-351)
-    3. every rank cuts the bin axis into `world` contiguous ranges of near-equal
-       global count -- all ranks compute the same cut from the same data, so no
-       further agreement step is needed; the same table gives every send and
-       receive count, no count exchange                              (host, tiny)
-    4. the local pairs are grouped by destination rank               (device kernel)
-    5. keys and rids are exchanged.  Two forms:
-       "peer"  steps 4 and 5 are ONE kernel: every rank maps the receive buffers of all
-               peers through CUDA IPC and the routing kernel's coalesced stores go over
-               NVLink / NVSwitch straight into the destination's HBM, at the offset the
-               all-gathered histograms assign to (source, destination); a one-word
-               all-reduce afterwards tells every rank that its buffer is complete
-       "nccl"  the routed pairs go to a local send buffer and through an NCCL
-               all-to-all (grouped ncclSend/ncclRecv) -- the unfused baseline, also what
-               the gloo tests exercise
-    6. every rank sorts what it received with the single-GPU sort, told the key range of
-       its share (msb64_b200_sort_device_range)                       (device kernels)
+"pipelined" (the product path; csrc/msb64_shard.cuh has the details)
+    1. every rank histograms the top 12 bits of its keys (+ min / max key)   (device kernel)
+    2. the histograms are all-gathered                                       (NCCL, or gloo)
+    3. every rank computes the same cut of the bin axis into world x 16 buckets -- ascending
+       key ranges of near-equal count, 16 sub-ranges per destination -- and from it every
+       count and offset on every GPU (msb64_b200_shard_plan; a narrow key span gets a
+       second histogram round on a window over [min, max])                   (host, C++)
+    4. ONE local MSD pass at HBM speed groups the rank's pairs by bucket     (device kernel)
+    5. sub-range by sub-range the copy engines move the buckets into the destination GPUs'
+       receive buffers over NVLink (CUDA IPC peer memory) and raise a flag behind each
+    6. while sub-ranges s+1.. are still travelling, the destination sorts sub-range s with the
+       single-GPU sort told its key range: NVLink and HBM work overlap.
+"peer"  one kernel routes a tile by destination and stores the runs straight into the peers'
+        HBM (fused route + exchange, msb64_b200_route_peer); the local sort starts when
+        everything has arrived.  Round 1's form, kept for comparison.
+"nccl"  route into a local send buffer + NCCL all-to-all (grouped ncclSend/ncclRecv) -- the
+        unfused baseline, and what the gloo tests drive with stand-in device steps.
 
 Afterwards rank r holds the r-th key range in ascending order and every key of rank r
 is <= every key of rank r+1 (the contract of the reference's sort() across NUMA
 nodes, msb_64.c:2180, include/msb_64.h:36).  Like the reference, the partition has a
 capacity factor (`fudge`): a rank that would receive more than capacity * fudge pairs
-raises Msb64Error(CAPACITY) where the reference's assert fires (msb_64.c:1574-1578).
+raises Msb64Error(CAPACITY) on every rank where the reference's assert fires
+(msb_64.c:1574-1578).
 
-The device steps go through the C ABI (include/msb64_b200.h, section 4) and there is
-no CPU implementation of them in this package.  `ops` exists so that the host logic
-above (steps 2, 3, 5 and the bookkeeping) can be exercised by multi-process tests on
-the gloo backend with stand-in device steps supplied by the test suite.
+The device steps go through the C ABI (include/msb64_b200.h, sections 4 and 5) and there is
+no CPU implementation of them in this package.  `ops` exists so that the host logic of the
+"nccl" form can be exercised by multi-process tests on the gloo backend with stand-in device
+steps supplied by the test suite.
 """
 from __future__ import annotations
 
@@ -155,10 +150,28 @@ class CudaOps:
         _m._raise(self.lib.msb64_b200_sort_device_range(keys.data_ptr(), rids.data_ptr(), n, ws.data_ptr(),
                                                         ws_bytes, self._stream(), None, key_lo, key_hi))
 
+    # -- pipelined form: one msb64_b200_shard per rank (include/msb64_b200.h section 5)
+    supports_pipelined = True
+
+    def shard_create(self, rank, world, capacity, fudge):
+        with self.torch.cuda.device(self.device):
+            h = self.lib.msb64_b200_shard_create(rank, world, capacity, C.c_double(fudge))
+        if not h:
+            raise _m.Msb64Error(-5, self.lib.msb64_b200_last_error().decode())
+        return h
+
+    def view(self, ptr, count):
+        """torch view of `count` int64 slots of library-owned device memory."""
+        return self.torch.as_tensor(_RawCuda(ptr, count), device=self.device)
+
 
 # --------------------------------------------------------------------- the sorter
 class ShardedSorter:
-    """Reusable buffers + the six steps above for `capacity` local pairs per rank."""
+    """Reusable buffers + the steps above for `capacity` local pairs per rank.
+
+    exchange: "pipelined" | "peer" | "nccl" | "auto" (pipelined where the device steps are the
+    CUDA library's, else nccl).  The collectives run on `group`; with a gloo group (two ranks
+    sharing one GPU in the tests, or a CPU control plane) they go through host memory."""
 
     def __init__(self, capacity: int, device=None, fudge: float = 1.125, bits: int = DEFAULT_BITS,
                  group=None, ops=None, exchange: str = "auto"):
@@ -168,6 +181,7 @@ class ShardedSorter:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.host_collectives = dist.is_initialized() and dist.get_backend(group) == "gloo"
         if self.world > 64:
             raise _m.Msb64Error(-2, "at most 64 ranks (msb64_b200_route destinations)")
         self.bits = int(bits)
@@ -183,50 +197,158 @@ class ShardedSorter:
         o = self.ops
         if not 4 <= self.bits <= 12:
             raise _m.Msb64Error(-2, "bits must be 4..12")
-        self.slots = (2 << self.bits) + 2              # room for the (bits+1)-bit window + min, max
-        self.hist = o.empty(self.slots)
-        self.all_hist = o.empty(self.world * self.slots)
-        if exchange not in ("auto", "peer", "nccl"):
-            raise _m.Msb64Error(-2, "exchange must be 'auto', 'peer' or 'nccl'")
+        if exchange not in ("auto", "pipelined", "peer", "nccl"):
+            raise _m.Msb64Error(-2, "exchange must be 'auto', 'pipelined', 'peer' or 'nccl'")
         self.exchange = "nccl"
         self._own = self._peer_keys = self._peer_rids = None
-        if self.world > 1 and exchange != "nccl" and getattr(o, "supports_peer", False):
-            self._setup_peer(exchange == "peer")
-        if self.exchange == "nccl":
-            self.recv_keys = o.empty(self.recv_cap)
-            self.recv_rids = o.empty(self.recv_cap)
-        # the sort's scratch doubles as the send buffer: the exchange is over before the
-        # local sort starts, and the sort treats its workspace as uninitialised
-        self.ws, self.ws_bytes = o.workspace(self.recv_cap)
-        words = self.ws[: (self.ws.numel() // 8) * 8].view(torch.int64)
-        assert words.numel() >= 2 * self.capacity, "workspace smaller than the send buffers"
-        self.send_keys = words[: self.capacity]
-        self.send_rids = words[self.capacity: 2 * self.capacity]
+        self._shard = None
         self.last_counts = None
+        self.last_times = None
+        pipelined_ok = getattr(o, "supports_pipelined", False)
+        if exchange == "pipelined" and not pipelined_ok:
+            raise _m.Msb64Error(-1, "the pipelined exchange needs the CUDA library's device steps")
+        if exchange in ("auto", "pipelined") and pipelined_ok:
+            self._setup_pipelined(exchange == "pipelined")
+        if self.exchange != "pipelined":
+            self.slots = (2 << self.bits) + 2              # room for the (bits+1)-bit window + min, max
+            self.hist = o.empty(self.slots)
+            self.all_hist = o.empty(self.world * self.slots)
+            if self.world > 1 and exchange == "peer" and getattr(o, "supports_peer", False):
+                self._setup_peer(True)
+            if self.exchange == "nccl":
+                self.recv_keys = o.empty(self.recv_cap)
+                self.recv_rids = o.empty(self.recv_cap)
+            # the sort's scratch doubles as the send buffer: the exchange is over before the
+            # local sort starts, and the sort treats its workspace as uninitialised
+            self.ws, self.ws_bytes = o.workspace(self.recv_cap)
+            words = self.ws[: (self.ws.numel() // 8) * 8].view(torch.int64)
+            assert words.numel() >= 2 * self.capacity, "workspace smaller than the send buffers"
+            self.send_keys = words[: self.capacity]
+            self.send_rids = words[self.capacity: 2 * self.capacity]
         # every rank knows every rank's receive capacity, so that an overflow is raised on
         # all ranks together (nobody is left waiting in the exchange)
-        caps = o.empty(self.world)
-        mine = o.empty(1)
-        mine.fill_(self.recv_cap)
-        if self.world > 1:
-            dist.all_gather_into_tensor(caps, mine, group=group)
-        else:
-            caps.copy_(mine)
-        self.recv_caps = caps.cpu().numpy().astype(np.int64)
+        self.recv_caps = self._all_gather_host(np.array([self.recv_cap], dtype=np.int64)).reshape(-1)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- collectives: rows of 8-byte words from every rank, on the host
+    def _all_gather_host(self, row: np.ndarray, device_row=None) -> np.ndarray:
+        """[world, len(row)] int64.  device_row: the same row as a device tensor (saves the
+        host round trip in front of an NCCL all-gather)."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return (row if device_row is None else device_row.cpu().numpy()).reshape(1, -1).copy()
+        if self.host_collectives:
+            mine = torch.from_numpy(np.ascontiguousarray(row if device_row is None else device_row.cpu().numpy()))
+            out = torch.empty(self.world * mine.numel(), dtype=mine.dtype)
+            dist.all_gather_into_tensor(out, mine, group=self.group)
+            return out.numpy().reshape(self.world, -1)
+        mine = device_row if device_row is not None else self.ops.from_numpy(np.ascontiguousarray(row))
+        out = self.ops.empty(self.world * mine.numel(), dtype=mine.dtype)
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out.cpu().numpy().reshape(self.world, -1)             # synchronises
+
+    def _all_agree(self, ok: bool) -> bool:
+        flags = self._all_gather_host(np.array([int(ok)], dtype=np.int64))
+        return bool(flags.min())
+
+    # -- pipelined exchange: one msb64_b200_shard, the peers' buffers mapped through CUDA IPC
+    def _setup_pipelined(self, required: bool):
+        o, lib = self.ops, self.ops.lib
+        ok, shard, detail = True, None, ""
+        try:
+            shard = o.shard_create(self.rank, self.world, self.capacity, self.fudge)
+        except _m.Msb64Error as e:
+            ok, detail = False, str(e)
+        handles = np.zeros(_m.MSB64_SHARD_HANDLE_BYTES // 8, dtype=np.int64)
+        if ok and self.world > 1:
+            buf = C.create_string_buffer(_m.MSB64_SHARD_HANDLE_BYTES)
+            if lib.msb64_b200_shard_export(shard, buf) == 0:
+                handles = np.frombuffer(buf.raw, dtype=np.int64).copy()
+            else:
+                ok, detail = False, lib.msb64_b200_last_error().decode()
+        # every rank takes part in every collective, whatever happened to it so far
+        allh = self._all_gather_host(handles)
+        if not self._all_agree(ok):
+            ok = False
+        if ok and self.world > 1:
+            raw = np.ascontiguousarray(allh).tobytes()
+            if lib.msb64_b200_shard_connect_ipc(shard, C.create_string_buffer(raw, len(raw))) != 0:
+                ok, detail = False, lib.msb64_b200_last_error().decode()
+        if self.world > 1 and not self._all_agree(ok):
+            ok = False
+        if not ok:
+            if shard:
+                lib.msb64_b200_shard_destroy(shard)
+            if required:
+                raise _m.Msb64Error(-1, "pipelined exchange unavailable on some rank (CUDA IPC / peer access / "
+                                        "memory): " + detail)
+            return
+        self._shard = shard
+        self.exchange = "pipelined"
+        self.slots = int(lib.msb64_b200_shard_slots())
+        self.recv_cap = int(lib.msb64_b200_shard_recv_capacity(shard))
+        self.hist = o.view(lib.msb64_b200_shard_hist(shard), self.slots)
+        self.recv_keys = o.view(lib.msb64_b200_shard_keys(shard), self.recv_cap)
+        self.recv_rids = o.view(lib.msb64_b200_shard_rids(shard), self.recv_cap)
+
+    def _sort_pipelined(self, keys, rids, n, timed):
+        torch, lib, shard = self.torch, self.ops.lib, self._shard
+        stream = self.ops._stream()
+        ev = None
+        if timed:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+        caps = (C.c_uint64 * self.world)(*[int(x) for x in self.recv_caps])
+        rc, reset = 1, 1
+        while rc == 1:
+            with torch.cuda.device(self.ops.device):
+                _m._raise(lib.msb64_b200_shard_histogram(shard, keys.data_ptr(), n, reset, stream))
+            # the all-gather also tells every rank that all of them are inside this call: nobody
+            # is still reading the receive buffers the peers are about to write into
+            allh = np.ascontiguousarray(self._all_gather_host(None, device_row=self.hist)).view(np.uint64)
+            rc = lib.msb64_b200_shard_plan(shard, allh.ctypes.data_as(C.POINTER(C.c_uint64)), caps, reset)
+            reset = 0
+        _m._raise(rc)                                    # CAPACITY: the same verdict on every rank
+        if ev:
+            ev[1].record()
+        with torch.cuda.device(self.ops.device):
+            _m._raise(lib.msb64_b200_shard_exchange_sort(shard, keys.data_ptr(), rids.data_ptr(), n, stream,
+                                                         1 if timed else 0))
+        total = int(lib.msb64_b200_shard_count(shard))
+        if ev:
+            ev[2].record()
+            torch.cuda.synchronize()
+            ms = (C.c_double * 5)()
+            _m._raise(lib.msb64_b200_shard_times(shard, ms))
+            self.last_times = {"plan": ev[0].elapsed_time(ev[1]), "route": ms[0], "first_wait": ms[1],
+                               "sort": ms[2], "exchange": ms[3], "step_device": ms[4],
+                               "total": ev[0].elapsed_time(ev[2]), "pairs_received": total,
+                               "pairs_sent_to_peers": None}
+        return self.recv_keys[:total], self.recv_rids[:total], total
 
     # -- peer-memory exchange: map every rank's receive buffers into this process
     def _setup_peer(self, required: bool):
-        torch, dist, o = self.torch, self.dist, self.ops
-        ok, opened = 1, []
+        o = self.ops
+        ok, opened = True, []
+        kp = rp = 0
+        handles = np.zeros(16, dtype=np.int64)
         try:
             kp, self.recv_keys = o.alloc_exportable(self.recv_cap)
             rp, self.recv_rids = o.alloc_exportable(self.recv_cap)
             self._own = (kp, rp)
-            mine = torch.frombuffer(bytearray(o.ipc_export(kp) + o.ipc_export(rp)), dtype=torch.uint8)
-            handles = torch.empty(128 * self.world, dtype=torch.uint8, device=self.recv_keys.device)
-            dist.all_gather_into_tensor(handles, mine.to(handles.device), group=self.group)
-            h = handles.cpu().numpy().tobytes()
-            keys_p, rids_p = [0] * self.world, [0] * self.world
+            handles = np.frombuffer(o.ipc_export(kp) + o.ipc_export(rp), dtype=np.int64).copy()
+        except _m.Msb64Error:
+            ok = False
+        # every rank takes part in every collective, whatever happened to it so far
+        h = np.ascontiguousarray(self._all_gather_host(handles)).tobytes()
+        ok = self._all_agree(ok)
+        keys_p, rids_p = [0] * self.world, [0] * self.world
+        if ok:
             for r in range(self.world):
                 if r == self.rank:
                     keys_p[r], rids_p[r] = kp, rp
@@ -235,17 +357,12 @@ class ShardedSorter:
                 b = o.ipc_open(h[128 * r + 64: 128 * r + 128])
                 opened += [x for x in (a, b) if x]
                 if not a or not b:
-                    ok = 0
+                    ok = False
                     break
                 keys_p[r], rids_p[r] = a, b
-        except _m.Msb64Error:
-            ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=self.hist.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        if int(flag.item()):
+        if self._all_agree(ok):
             self.exchange = "peer"
             self._peer_keys, self._peer_rids, self._opened = keys_p, rids_p, opened
-            self._done = torch.zeros(1, dtype=torch.int32, device=self.hist.device)
             return
         for x in opened:
             o.ipc_close(x)
@@ -260,10 +377,16 @@ class ShardedSorter:
     def close(self):
         """Unmap the peers' buffers and release the exported ones (collective: every rank
         must have finished using the sorter)."""
-        if self.exchange == "peer" and self._own:
-            self.torch.cuda.synchronize()
+        if self._shard is not None or (self.exchange == "peer" and self._own):
+            if self.torch.cuda.is_available():
+                self.torch.cuda.synchronize()
             if self.world > 1:
-                self.dist.barrier(group=self.group)
+                self._all_agree(True)                         # a barrier on whatever backend the group has
+        if self._shard is not None:
+            self.hist = self.recv_keys = self.recv_rids = None
+            self.ops.lib.msb64_b200_shard_destroy(self._shard)
+            self._shard = None
+        if self.exchange == "peer" and self._own:
             for x in self._opened:
                 self.ops.ipc_close(x)
             self.recv_keys = self.recv_rids = None
@@ -271,18 +394,21 @@ class ShardedSorter:
                 self.ops.free_exportable(x)
             self._own = None
 
-    # -- steps 1-3
+    def __del__(self):
+        # single-rank sorters own nothing a peer has mapped: release without a collective
+        try:
+            if self.world == 1 and self._shard is not None:
+                self.close()
+        except Exception:
+            pass
+
+    # -- steps 1-3 ("peer" and "nccl" forms)
     def _histograms(self, keys, n, shift, bits, origin):
         """Per-rank histograms [world, 2^bits] of the given digit and the global min / max key."""
         nb = 1 << bits
         self.ops.digit_histogram(keys, n, shift, bits, origin, self.hist, self.hist[nb: nb + 2])
-        if self.world > 1:
-            self.dist.all_gather_into_tensor(self.all_hist, self.hist, group=self.group)
-            hists = self.all_hist
-        else:
-            hists = self.hist
-        h = hists.cpu().numpy().reshape(self.world, self.slots)           # synchronises
-        mm = h[:, nb: nb + 2].view(np.uint64)
+        h = self._all_gather_host(None, device_row=self.hist)
+        mm = np.ascontiguousarray(h[:, nb: nb + 2]).view(np.uint64)
         have = mm[:, 0] <= mm[:, 1]                                       # ranks that hold any key
         gmin = int(mm[have, 0].min()) if have.any() else 0
         gmax = int(mm[have, 1].max()) if have.any() else 0
@@ -311,15 +437,17 @@ class ShardedSorter:
         Returns (keys, rids, count) of this rank's key range, sorted; the tensors are
         views of the sorter's receive buffers, valid until the next call.
         timed=True (CUDA ops only) records device times of the steps in self.last_times
-        (milliseconds: plan, exchange, barrier, local_sort) and synchronises."""
+        (milliseconds) and synchronises."""
         torch, dist = self.torch, self.dist
+        n = keys.numel() if n is None else int(n)
+        if n > self.capacity:
+            raise _m.Msb64Error(-2, f"{n} pairs exceed the sorter's capacity {self.capacity}")
+        if self.exchange == "pipelined":
+            return self._sort_pipelined(keys, rids, n, timed)
         ev = None
         if timed:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             ev[0].record()
-        n = keys.numel() if n is None else int(n)
-        if n > self.capacity:
-            raise _m.Msb64Error(-2, f"{n} pairs exceed the sorter's capacity {self.capacity}")
         shift, bits, origin, table, counts = self.plan(keys, n)
         if ev:
             ev[1].record()
@@ -347,7 +475,8 @@ class ShardedSorter:
                                 self._peer_keys, self._peer_rids)
             if ev:
                 ev[2].record()
-            dist.all_reduce(self._done, group=self.group)      # every rank's stores have landed
+            torch.cuda.current_stream().synchronize()          # this rank's stores have left
+            self._all_agree(True)                              # ... and so have everybody's
         else:
             starts = np.concatenate([[0], np.cumsum(send)[:-1]]).astype(np.uint32)
             cursors = self.ops.from_numpy(starts.view(np.int32))
@@ -382,18 +511,14 @@ class ShardedSorter:
     # -- acceptance across ranks (the cross-node half of check(), msb_64.c:2485-2495)
     def boundaries_ordered(self, out_keys, out_n: int) -> bool:
         """True on every rank iff every rank's last key <= the next non-empty rank's first."""
-        torch, dist = self.torch, self.dist
         if self.world == 1:
             return True
-        edge = torch.zeros(3, dtype=torch.int64, device=out_keys.device)
+        edge = np.zeros(3, dtype=np.int64)
         if out_n:
-            edge[0] = out_keys[0]
-            edge[1] = out_keys[out_n - 1]
-            edge[2] = 1
-        edges = torch.empty(3 * self.world, dtype=torch.int64, device=out_keys.device)
-        dist.all_gather_into_tensor(edges, edge, group=self.group)
-        e = edges.cpu().numpy().reshape(self.world, 3)
-        first, last = e[:, 0].view(np.uint64), e[:, 1].view(np.uint64)
+            ends = out_keys[[0, out_n - 1]].cpu().numpy()
+            edge[0], edge[1], edge[2] = ends[0], ends[1], 1
+        e = self._all_gather_host(edge)
+        first, last = np.ascontiguousarray(e[:, 0]).view(np.uint64), np.ascontiguousarray(e[:, 1]).view(np.uint64)
         prev = None
         for r in range(self.world):
             if not e[r, 2]:

@@ -25,6 +25,7 @@ _u64pp = C.POINTER(_u64p)
 
 MSB64_OK = 0
 MSB64_MAX_PAIRS = 0xFFFF0000
+MSB64_SHARD_HANDLE_BYTES = 192
 PHASES = ("histogram", "plan", "scatter", "local_sort", "copy_home")
 ERRORS = {-1: "CUDA", -2: "ARG", -3: "TOO_BIG", -4: "CAPACITY", -5: "NOMEM", -6: "INTERNAL"}
 
@@ -41,6 +42,13 @@ EXPORTS = (
     "msb64_b200_stream_sync", "msb64_b200_fill", "msb64_b200_check",
     "msb64_b200_digit_histogram", "msb64_b200_route", "msb64_b200_route_peer",
     "msb64_b200_ipc_export", "msb64_b200_ipc_open", "msb64_b200_ipc_close",
+    "msb64_b200_last_status",
+    "msb64_b200_shard_create", "msb64_b200_shard_destroy", "msb64_b200_shard_export",
+    "msb64_b200_shard_connect_ipc", "msb64_b200_shard_connect_local", "msb64_b200_shard_slots",
+    "msb64_b200_shard_subs", "msb64_b200_shard_histogram", "msb64_b200_shard_hist",
+    "msb64_b200_shard_plan", "msb64_b200_shard_plan_host", "msb64_b200_shard_exchange_sort",
+    "msb64_b200_shard_count", "msb64_b200_shard_recv_capacity", "msb64_b200_shard_keys",
+    "msb64_b200_shard_rids", "msb64_b200_shard_key_range", "msb64_b200_shard_times",
 )
 
 
@@ -133,8 +141,70 @@ def load_library() -> C.CDLL:
     L.msb64_b200_ipc_open.argtypes = [C.c_void_p]
     L.msb64_b200_ipc_close.restype = C.c_int
     L.msb64_b200_ipc_close.argtypes = [C.c_void_p]
+    L.msb64_b200_last_status.restype = C.c_int
+    L.msb64_b200_last_status.argtypes = [C.c_void_p]
+    # section 5: the sort sharded over several GPUs
+    L.msb64_b200_shard_create.restype = C.c_void_p
+    L.msb64_b200_shard_create.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_double]
+    L.msb64_b200_shard_destroy.restype = None
+    L.msb64_b200_shard_destroy.argtypes = [C.c_void_p]
+    L.msb64_b200_shard_export.restype = C.c_int
+    L.msb64_b200_shard_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.msb64_b200_shard_connect_ipc.restype = C.c_int
+    L.msb64_b200_shard_connect_ipc.argtypes = [C.c_void_p, C.c_void_p]
+    L.msb64_b200_shard_connect_local.restype = C.c_int
+    L.msb64_b200_shard_connect_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.msb64_b200_shard_slots.restype = C.c_int
+    L.msb64_b200_shard_subs.restype = C.c_int
+    L.msb64_b200_shard_subs.argtypes = [C.c_int]
+    L.msb64_b200_shard_histogram.restype = C.c_int
+    L.msb64_b200_shard_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    L.msb64_b200_shard_hist.restype = C.c_void_p
+    L.msb64_b200_shard_hist.argtypes = [C.c_void_p]
+    L.msb64_b200_shard_plan.restype = C.c_int
+    L.msb64_b200_shard_plan.argtypes = [C.c_void_p, _u64p, _u64p, C.c_int]
+    L.msb64_b200_shard_plan_host.restype = C.c_int
+    L.msb64_b200_shard_plan_host.argtypes = [_u64p, C.c_int, _u64p, C.c_int, C.POINTER(C.c_int),
+                                             C.POINTER(C.c_int), _u64p, C.c_void_p, _u64p]
+    L.msb64_b200_shard_exchange_sort.restype = C.c_int
+    L.msb64_b200_shard_exchange_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                 C.c_void_p, C.c_int]
+    for name in ("count", "recv_capacity"):
+        f = getattr(L, f"msb64_b200_shard_{name}")
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p]
+    for name in ("keys", "rids"):
+        f = getattr(L, f"msb64_b200_shard_{name}")
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p]
+    L.msb64_b200_shard_key_range.restype = C.c_int
+    L.msb64_b200_shard_key_range.argtypes = [C.c_void_p, _u64p, _u64p]
+    L.msb64_b200_shard_times.restype = C.c_int
+    L.msb64_b200_shard_times.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     _lib = L
     return L
+
+
+def shard_plan_host(hists: np.ndarray, recv_caps, may_retry: bool = True, shift: int = 52, bits: int = 12,
+                    origin: int = 0):
+    """The plan of the sharded sort on the host (msb64_b200_shard_plan_host, no device needed).
+
+    hists: [world, msb64_b200_shard_slots()] uint64 rows (counts of the digit (key >> shift) -
+    origin, then min and max key at [2^bits], [2^bits + 1]).  Returns (rc, shift, bits, origin,
+    table, counts): rc 0 = accepted (table[bin] = bucket = destination * subs + sub-range,
+    counts[source][bucket]), 1 = histogram again with the returned digit, -4 = CAPACITY."""
+    L = load_library()
+    hists = np.ascontiguousarray(hists, dtype=np.uint64)
+    world = hists.shape[0]
+    assert hists.shape[1] == L.msb64_b200_shard_slots()
+    subs = L.msb64_b200_shard_subs(world)
+    caps = (C.c_uint64 * world)(*[int(x) for x in recv_caps])
+    sh, bi, org = C.c_int(shift), C.c_int(bits), C.c_uint64(origin)
+    table = np.zeros(2 << 12, dtype=np.uint8)
+    counts = np.zeros((world, world * subs), dtype=np.uint64)
+    rc = L.msb64_b200_shard_plan_host(hists.ctypes.data_as(_u64p), world, caps, int(may_retry), C.byref(sh),
+                                      C.byref(bi), C.byref(org), table.ctypes.data, counts.ctypes.data_as(_u64p))
+    return rc, sh.value, bi.value, org.value, table[: 1 << bi.value], counts
 
 
 def _raise(rc: int) -> None:

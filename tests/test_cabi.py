@@ -127,3 +127,96 @@ def test_range_schedule_invariants(msb):
             assert sum(bits[1:]) >= shift0, (lo, hi, n, bits, shift0)
     # the full range reproduces the default schedule
     assert msb.get_range_schedule(1 << 30, 0, (1 << 64) - 1)[0] == msb.get_schedule(1 << 30)
+
+
+def test_dropin_program_links(msb):
+    """tests/c/dropin.c includes the REFERENCE's include/msb_64.h verbatim and links against
+    libmsb64_b200.so: sort() and mamalloc() resolve to this library (run: tests/test_gpu_parity.py)."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "c"))
+    import build_dropin
+    if not os.path.exists(os.path.join(build_dropin.REF_INCLUDE, "msb_64.h")):
+        pytest.skip("the reference header is not on this box; the binary was built where it is")
+    path = build_dropin.build()
+    assert path and os.path.exists(path)
+    src = open(os.path.join(ROOT, "tests", "c", "dropin.c")).read()
+    assert '#include "msb_64.h"' in src and "msb64_b200" not in src.split("*/", 1)[1], \
+        "the program must be written against the reference header only"
+    und = subprocess.run(["nm", "-D", "--undefined-only", path], capture_output=True, text=True).stdout
+    assert " sort" in und and " mamalloc" in und
+    ldd = subprocess.run(["ldd", path], capture_output=True, text=True).stdout
+    assert "libmsb64_b200.so" in ldd and "not found" not in ldd
+
+
+def _hist_rows(msb, key_sets, shift=52, bits=12, origin=0):
+    slots = msb.load_library().msb64_b200_shard_slots()
+    h = np.zeros((len(key_sets), slots), dtype=np.uint64)
+    nb = 1 << bits
+    for r, k in enumerate(key_sets):
+        d = ((k >> np.uint64(shift)) - np.uint64(origin)) & np.uint64(nb - 1)
+        h[r, :nb] = np.bincount(d.astype(np.int64), minlength=nb)
+        h[r, nb] = k.min() if k.size else np.uint64((1 << 64) - 1)
+        h[r, nb + 1] = k.max() if k.size else 0
+    return h
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8, 16, 64])
+def test_shard_plan_host(msb, world):
+    """The plan of the sharded sort (msb64_b200_shard_plan_host; host only): monotone bucket
+    table, counts that match the histograms, destinations balanced, sub-ranges balanced."""
+    from inplacemsdradixsort_b200 import msb64
+    lib = msb.load_library()
+    subs = lib.msb64_b200_shard_subs(world)
+    assert subs >= 1 and world * subs <= 256 and (world > 16 or subs == 16)
+    rng = np.random.default_rng(world)
+    per = 40_000
+    ks = [rng.integers(0, 1 << 64, size=per + 13 * r, dtype=np.uint64) for r in range(world)]
+    h = _hist_rows(msb, ks)
+    caps = [int(per * 1.3)] * world
+    rc, shift, bits, origin, table, counts = msb64.shard_plan_host(h, caps)
+    assert (rc, shift, bits, origin) == (0, 52, 12, 0)
+    assert table.size == 4096 and np.all(np.diff(table.astype(np.int64)) >= 0) and int(table.max()) < world * subs
+    digit = [(k >> np.uint64(52)).astype(np.int64) for k in ks]
+    for r in range(world):
+        assert np.array_equal(counts[r], np.bincount(table[digit[r]], minlength=world * subs).astype(np.uint64))
+    per_dest = counts.sum(axis=0).reshape(world, subs).sum(axis=1)
+    total = sum(k.size for k in ks)
+    assert per_dest.sum() == total
+    assert per_dest.max() - per_dest.min() <= 4 * (total / 4096 + 200)          # bins are never split
+    if world <= 8:
+        per_sub = counts.sum(axis=0).astype(np.int64)
+        assert per_sub.max() - per_sub.min() <= 4 * (total / 4096 + 200)
+
+
+def test_shard_plan_host_window_and_capacity(msb):
+    from inplacemsdradixsort_b200 import msb64
+    rng = np.random.default_rng(9)
+    world, per = 4, 30_000
+    # keys that share their top bits: the first plan asks for a window on the keys' span
+    ks = [(rng.integers(0, 1 << 64, size=per, dtype=np.uint64) & np.uint64((1 << 24) - 1)) + np.uint64(1 << 40)
+          for _ in range(world)]
+    caps = [int(per * 1.3)] * world
+    rc, shift, bits, origin, _, _ = msb64.shard_plan_host(_hist_rows(msb, ks), caps)
+    assert rc == 1 and bits == 13 and shift == 12 and origin == int(min(k.min() for k in ks)) >> 12
+    rc, s2, b2, o2, table, counts = msb64.shard_plan_host(_hist_rows(msb, ks, shift, bits, origin), caps,
+                                                          may_retry=False, shift=shift, bits=bits, origin=origin)
+    assert (rc, s2, b2, o2) == (0, shift, bits, origin)
+    assert table.size == 1 << 13
+    per_dest = counts.sum(axis=0).reshape(world, -1).sum(axis=1)
+    assert per_dest.max() <= caps[0] and per_dest.sum() == world * per
+    # all keys equal: no cut can spread them -- CAPACITY, like the reference's assert (msb_64.c:1574)
+    eq = [np.full(per, 77, dtype=np.uint64) for _ in range(world)]
+    rc, shift, bits, origin, _, _ = msb64.shard_plan_host(_hist_rows(msb, eq), caps)
+    if rc == 1:
+        rc = msb64.shard_plan_host(_hist_rows(msb, eq, shift, bits, origin), caps, may_retry=False,
+                                   shift=shift, bits=bits, origin=origin)[0]
+    assert rc == -4
+    assert "capacity" in msb.load_library().msb64_b200_last_error().decode()
+    # ranks without keys take part
+    some = [ks[0], np.zeros(0, np.uint64), ks[2], np.zeros(0, np.uint64)]
+    rc, shift, bits, origin, _, _ = msb64.shard_plan_host(_hist_rows(msb, some), caps)
+    assert rc == 1
+    rc, _, _, _, _, counts = msb64.shard_plan_host(_hist_rows(msb, some, shift, bits, origin), caps, may_retry=False,
+                                                   shift=shift, bits=bits, origin=origin)
+    assert rc == 0 and counts[1].sum() == 0 and counts.sum() == 2 * per

@@ -80,28 +80,58 @@ def test_route_groups_by_destination(gpu, kind, n, ndest):
         assert np.array_equal(gr[lo:hi][got], rids[sel][want]), f"destination {d}: rids differ"
 
 
-@pytest.mark.parametrize("kind", ["uniform", "low24", "dup16"])
-def test_sharded_sorter_single_gpu(gpu, oracle, kind):
+def _oracle_sorted(oracle, keys, rids):
+    n = keys.size
+    wk = np.concatenate([keys, np.zeros(n // 2 + 64, np.uint64)])
+    wr = np.concatenate([rids, np.zeros(n // 2 + 64, np.uint64)])
+    oracle.sort([wk], [wr], [n])
+    return wk[:n], wr[:n]
+
+
+@pytest.mark.parametrize("exchange", ["pipelined", "nccl"])
+@pytest.mark.parametrize("kind", ["uniform", "low24", "dup16", "sorted", "midbits", "skew", "equal", "outlier"])
+def test_sharded_sorter_single_gpu(gpu, oracle, kind, exchange):
+    """world = 1: the pipelined form still runs its bucket pass and the 16 sub-range sorts."""
     import torch
     from inplacemsdradixsort_b200.distributed import ShardedSorter
     n = 200_003
     keys = make(kind, n, seed=3)
     rids = np.arange(n, dtype=np.uint64)
     dev = torch.device("cuda", 0)
-    s = ShardedSorter(n, dev)
-    kt = torch.from_numpy(keys.view(np.int64)).to(dev)
-    rt = torch.from_numpy(rids.view(np.int64)).to(dev)
-    ok_, or_, cnt = s.sort(kt, rt)
-    torch.cuda.synchronize()
-    assert cnt == n
-    gk = ok_.cpu().numpy().view(np.uint64)
-    gr = or_.cpu().numpy().view(np.uint64)
-    wk = np.concatenate([keys, np.zeros(n // 2 + 64, np.uint64)])
-    wr = np.concatenate([rids, np.zeros(n // 2 + 64, np.uint64)])
-    oracle.sort([wk], [wr], [n])
-    assert np.array_equal(gk, wk[:n])
-    assert np.array_equal(gr[np.lexsort((gr, gk))], wr[:n][np.lexsort((wr[:n], wk[:n]))])
-    assert s.boundaries_ordered(ok_, cnt)
+    with ShardedSorter(n, dev, exchange=exchange) as s:
+        assert s.exchange == exchange
+        kt = torch.from_numpy(keys.view(np.int64)).to(dev)
+        rt = torch.from_numpy(rids.view(np.int64)).to(dev)
+        for _ in range(2):                                   # twice through the same buffers
+            ok_, or_, cnt = s.sort(kt, rt)
+            torch.cuda.synchronize()
+            assert cnt == n
+            gk = ok_.cpu().numpy().view(np.uint64)
+            gr = or_.cpu().numpy().view(np.uint64)
+            wk, wr = _oracle_sorted(oracle, keys, rids)
+            assert np.array_equal(gk, wk)
+            assert np.array_equal(gr[np.lexsort((gr, gk))], wr[np.lexsort((wr, wk))])
+            assert s.boundaries_ordered(ok_, cnt)
+        assert gpu.load_library().msb64_b200_last_status(None) == 0
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 4097, 1 << 20, 3_000_001])
+def test_pipelined_sizes_single_gpu(gpu, n):
+    import torch
+    from inplacemsdradixsort_b200.distributed import ShardedSorter
+    dev = torch.device("cuda", 0)
+    keys = make("uniform", n, seed=11)
+    rids = np.arange(n, dtype=np.uint64)
+    with ShardedSorter(max(n, 1), dev, exchange="pipelined") as s:
+        ok_, or_, cnt = s.sort(torch.from_numpy(keys.view(np.int64)).to(dev),
+                               torch.from_numpy(rids.view(np.int64)).to(dev), n=n)
+        torch.cuda.synchronize()
+        assert cnt == n
+        gk = ok_.cpu().numpy().view(np.uint64)
+        gr = or_.cpu().numpy().view(np.uint64)
+        order = np.lexsort((rids, keys))
+        assert np.array_equal(gk, keys[order])
+        assert np.array_equal(gr[np.lexsort((gr, gk))], rids[order])
 
 
 def _free_port():
@@ -142,7 +172,68 @@ def _nccl_worker(rank, world, port, kind, n, exchange, result):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def _shared_gpu_worker(rank, world, port, kind, n, exchange, result):
+    """`world` processes on cuda:0: collectives over gloo (host), the exchange over CUDA IPC
+    mappings of the other processes' buffers on the same device -- the N > 1 code path of the
+    product on a box with a single GPU."""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from inplacemsdradixsort_b200.distributed import ShardedSorter
+        n_local = n + 1000 * rank
+        s = ShardedSorter(n_local, dev, fudge=1.3, exchange=exchange)
+        assert s.exchange == exchange
+        outs = []
+        for it in range(2):                                  # the peers write into the same buffers again
+            keys = make(kind, n_local, seed=40 + rank + 100 * it)
+            rids = np.arange(n_local, dtype=np.uint64) + np.uint64(rank << 40)
+            ok_, or_, cnt = s.sort(torch.from_numpy(keys.view(np.int64)).to(dev),
+                                   torch.from_numpy(rids.view(np.int64)).to(dev))
+            ordered = s.boundaries_ordered(ok_, cnt)
+            torch.cuda.synchronize()
+            outs.append((ok_.cpu().numpy().view(np.uint64).copy(), or_.cpu().numpy().view(np.uint64).copy(),
+                         keys, rids, ordered))
+        result[rank] = outs
+        s.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _check_global(res, it, oracle=None):
+    all_k = np.concatenate([r[it][2] for r in res])
+    all_r = np.concatenate([r[it][3] for r in res])
+    out_k = np.concatenate([r[it][0] for r in res])
+    out_r = np.concatenate([r[it][1] for r in res])
+    order = np.lexsort((all_r, all_k))
+    assert np.array_equal(out_k, all_k[order])
+    if oracle is not None:
+        wk, _ = _oracle_sorted(oracle, all_k, all_r)
+        assert np.array_equal(out_k, wk), "keys differ from the oracle's global sort"
+    assert np.array_equal(out_r[np.lexsort((out_r, out_k))], all_r[order])
+    assert all(r[it][4] for r in res)
+
+
+@pytest.mark.parametrize("exchange,world", [("pipelined", 2), ("pipelined", 3), ("peer", 2)])
+@pytest.mark.parametrize("kind", ["uniform", "low24", "midbits", "sorted", "dup16"])
+def test_sharded_sorter_ranks_sharing_one_gpu(gpu, oracle, kind, exchange, world):
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_shared_gpu_worker, args=(world, _free_port(), kind, 300_003, exchange, result), nprocs=world, join=True)
+    res = [result[r] for r in range(world)]
+    for it in range(2):
+        _check_global(res, it, oracle)
+    # balance: bins are never split, so only uniform keys promise near-equal shares
+    if kind == "uniform":
+        sizes = [r[0][0].size for r in res]
+        assert max(sizes) - min(sizes) < 0.05 * sum(sizes)
+
+
+@pytest.mark.parametrize("exchange", ["pipelined", "peer", "nccl"])
 @pytest.mark.parametrize("kind", ["uniform", "sorted", "low24", "midbits"])
 def test_sharded_sorter_two_gpus_nccl(gpu, kind, exchange):
     import torch

@@ -5,10 +5,15 @@ sorted key sequence exactly; rids must carry the same (key, rid) multiset (MSD r
 sort is not stable, neither here nor in the reference), which is checked exactly at
 these sizes: sorting rids inside every run of equal keys on both sides and comparing.
 """
+import os
+import sys
+
 import numpy as np
 import pytest
 
 from inputs import KINDS, make
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -232,3 +237,58 @@ def test_device_sort_at_odd_offsets(gpu):
         assert np.array_equal(out_k[off: off + n], np.sort(keys))
         got_r = out_r[off: off + n]
         assert np.array_equal(keys[got_r.astype(np.int64)], out_k[off: off + n]), "rid does not point at its key"
+
+
+@pytest.mark.parametrize("numa,virtual,kind", [(1, 0, 0), (2, 0, 0), (3, 0, 2), (2, 1, 0), (3, 1, 1), (4, 1, 2)])
+def test_dropin_c_program(gpu, numa, virtual, kind):
+    """A C program that includes the reference's include/msb_64.h verbatim, linked against
+    libmsb64_b200.so (tests/c/dropin.c): calls mamalloc() + sort() and checks the result.
+    virtual = 1: the nodes are sorted as shards sharing the visible GPUs (the multi-GPU path of
+    sort(), msb_64.c:2261-2275 across NUMA nodes) even on a box with one GPU."""
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests", "c"))
+    import build_dropin
+    path = build_dropin.build()
+    assert path and os.path.exists(path), "tests/c/_build/dropin must be built where the reference header is"
+    env = dict(os.environ)
+    env.pop("MSB64_B200_VIRTUAL_SHARDS", None)
+    env["MSB64_B200_SINGLE_DEVICE"] = "1"
+    if virtual:
+        env["MSB64_B200_VIRTUAL_SHARDS"] = "1"
+        env.pop("MSB64_B200_SINGLE_DEVICE")
+    res = subprocess.run([path, str(numa), "400003", "1.5", str(kind)], capture_output=True, text=True, env=env,
+                         timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "dropin ok" in res.stdout
+
+
+@pytest.mark.parametrize("kind", ["uniform", "low24", "dup1000", "sorted"])
+@pytest.mark.parametrize("numa", [2, 5])
+def test_sort_over_shards(gpu, oracle, kind, numa):
+    """sort() with numa arrays on numa (virtual) GPU shards: node n gets the n-th key range."""
+    per = 150_000
+    fudge = 1.6
+    keys = [np.concatenate([make(kind, per + 31 * i, seed=70 + i), np.zeros(per, dtype=np.uint64)]) for i in range(numa)]
+    rids = [np.concatenate([np.arange(per + 31 * i, dtype=np.uint64) + np.uint64(i << 40), np.zeros(per, dtype=np.uint64)])
+            for i in range(numa)]
+    size = [per + 31 * i for i in range(numa)]
+    all_k = np.concatenate([k[:s] for k, s in zip(keys, size)])
+    all_r = np.concatenate([r[:s] for r, s in zip(rids, size)])
+    os.environ["MSB64_B200_VIRTUAL_SHARDS"] = "1"
+    try:
+        phases = gpu.sort(keys, rids, size, numa=numa, fudge=fudge)
+    finally:
+        del os.environ["MSB64_B200_VIRTUAL_SHARDS"]
+    assert any("exchange" in p for p in phases), f"the sharded path did not run: {phases}"
+    assert sum(size) == all_k.size
+    out_k = np.concatenate([keys[i][:size[i]] for i in range(numa)])
+    out_r = np.concatenate([rids[i][:size[i]] for i in range(numa)])
+    n = all_k.size
+    wk = np.concatenate([all_k, np.zeros(n // 2 + 64, np.uint64)])
+    wr = np.concatenate([all_r, np.zeros(n // 2 + 64, np.uint64)])
+    oracle.sort([wk], [wr], [n])
+    assert np.array_equal(out_k, wk[:n])
+    ck, cr = canon(out_k, out_r)
+    ek, er = canon(all_k, all_r)
+    assert np.array_equal(cr, er)
+    gpu.check(keys, rids, size, numa=numa)
