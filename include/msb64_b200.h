@@ -171,6 +171,8 @@ int msb64_b200_stream_sync(void *stream);
  * reference's MT19937-64 of rand.c, which is sequential):
  *   kind 0: uniform 64-bit keys            kind 1: keys & mask (mask = param)
  *   kind 2: `param` distinct values        kind 3: ascending   kind 4: descending
+ *   kind 5: clusters of ~3000 keys that differ in their low 2 bits only
+ *   kind 6: 12-bit keys and one outlier    kind 7: zipf-like (exponent 1.3)
  * rids = element index when d_rids != NULL. */
 int msb64_b200_fill(uint64_t *d_keys, uint64_t *d_rids, uint64_t n,
 		    int kind, uint64_t seed, uint64_t param, void *stream);
@@ -283,6 +285,7 @@ int msb64_b200_shard_plan_host(const uint64_t *all_hists, int world, const uint6
 int msb64_b200_shard_exchange_sort(msb64_b200_shard *shard, const uint64_t *d_keys,
 				   const uint64_t *d_rids, uint64_t n, void *stream, int timed);
 uint64_t msb64_b200_shard_count(const msb64_b200_shard *shard);
+uint64_t msb64_b200_shard_sent(const msb64_b200_shard *shard);	/* pairs the last step sent to other GPUs */
 uint64_t msb64_b200_shard_recv_capacity(const msb64_b200_shard *shard);
 uint64_t *msb64_b200_shard_keys(msb64_b200_shard *shard);
 uint64_t *msb64_b200_shard_rids(msb64_b200_shard *shard);

@@ -490,6 +490,18 @@ __global__ void fill_kernel(uint64_t *keys, uint64_t *rids, uint64_t n, int kind
 		case 2: k = mix64((x % (param ? param : 1)) + 0x51ed27ull); break;
 		case 3: k = i * (param ? param : 1); break;
 		case 4: k = (n - 1 - i) * (param ? param : 1); break;
+		case 5: {       // clustered: ~3000 keys share their 52 high bits and differ in the low 2
+			const uint64_t clusters = n / 3000 + 1;
+			k = (mix64((x % clusters) + 0x1234567ull) & ~0xfffull) | (mix64(x) & 3ull);
+			break;
+		}
+		case 6: k = i == n / 2 ? (1ull << 63) : (x & 0xfffull); break;       // one outlier, the rest 12 bits
+		case 7: {       // zipf-like (exponent 1.3): value = floor(u^(-1/0.3)), spread by a multiplier
+			const double u = (double(x >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+			const double z = floor(pow(u, -1.0 / 0.3));
+			k = (z >= 9.2e18 ? 0x7fffffffffffffffull : uint64_t(z)) * 0x9e3779b97f4a7c15ull;
+			break;
+		}
 		default: k = x;
 		}
 		keys[i] = k;

@@ -196,7 +196,7 @@ struct msb64_b200_shard {
 	cudaEvent_t tev[6] = {nullptr};                         // timing: start, routed, first sub-range in, sorted, exchange end x2
 	uint32_t epoch = 0;
 	ShardPlan plan;
-	uint64_t recv_total = 0;
+	uint64_t recv_total = 0, sent_total = 0;
 	uint64_t key_lo = 0, key_hi = ~0ull;
 	bool timed = false;
 	// only when the shard is driven by the host-array sort() of this process (msb64_b200.cu)
@@ -345,6 +345,7 @@ int shard_route_exchange_locked(msb64_b200_shard &S, const uint64_t *d_keys, con
 			cursors[b] = uint32_t(at);
 			at += P.counts[size_t(me) * nbk + b];
 		}
+	S.sent_total = at;
 	for (int s = 0; s < subs; ++s) cursors[me * subs + s] = uint32_t(P.recv_offset(me, s, me));
 	CUDA_TRY(cudaMemcpyAsync(S.d_table, P.table.data(), P.table.size(), cudaMemcpyHostToDevice, st));
 	CUDA_TRY(cudaMemcpyAsync(S.d_cursors, cursors.data(), SHARD_MAX_BUCKETS * sizeof(uint32_t),
@@ -639,6 +640,7 @@ int msb64_b200_shard_exchange_sort(msb64_b200_shard *S, const uint64_t *d_keys, 
 }
 
 uint64_t msb64_b200_shard_count(const msb64_b200_shard *S) { return S ? S->recv_total : 0; }
+uint64_t msb64_b200_shard_sent(const msb64_b200_shard *S) { return S ? S->sent_total : 0; }
 uint64_t msb64_b200_shard_recv_capacity(const msb64_b200_shard *S) { return S ? S->recv_cap : 0; }
 uint64_t *msb64_b200_shard_keys(msb64_b200_shard *S) { return S ? S->recv_keys : nullptr; }
 uint64_t *msb64_b200_shard_rids(msb64_b200_shard *S) { return S ? S->recv_rids : nullptr; }

@@ -328,7 +328,7 @@ class ShardedSorter:
             self.last_times = {"plan": ev[0].elapsed_time(ev[1]), "route": ms[0], "first_wait": ms[1],
                                "sort": ms[2], "exchange": ms[3], "step_device": ms[4],
                                "total": ev[0].elapsed_time(ev[2]), "pairs_received": total,
-                               "pairs_sent_to_peers": None}
+                               "pairs_sent_to_peers": int(lib.msb64_b200_shard_sent(shard))}
         return self.recv_keys[:total], self.recv_rids[:total], total
 
     # -- peer-memory exchange: map every rank's receive buffers into this process
