@@ -29,6 +29,7 @@
 #include "msb64_histogram.cuh"
 #include "msb64_local_sort.cuh"
 #include "msb64_local_packed.cuh"
+#include "msb64_local_packed2.cuh"
 #include "msb64_plan.cuh"
 #include "msb64_scatter.cuh"
 #include "msb64_route.cuh"
@@ -41,6 +42,13 @@ using namespace msb64;
 #endif
 #ifndef MSB64_SCATTER_MINB
 #define MSB64_SCATTER_MINB 3
+#endif
+#ifdef MSB64_PACKED_V1
+#define MSB64_PACKED_KERNEL local_sort_packed_kernel
+#define MSB64_PACKED_SMEM PACKED_SMEM
+#else
+#define MSB64_PACKED_KERNEL local_sort_packed2_kernel
+#define MSB64_PACKED_SMEM PACKED2_SMEM
 #endif
 constexpr int SCATTER_THREADS = MSB64_SCATTER_THREADS;
 constexpr int SCATTER_MINB = MSB64_SCATTER_MINB;
@@ -235,10 +243,10 @@ int device_get(Device **out)
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.local_blocks, local_sort_kernel,
 							       LOCAL_THREADS, LOCAL_SMEM));
 	if (D.local_blocks < 1) return fail(MSB64_ERR_CUDA, "local sort does not fit on an SM%s");
-	CUDA_TRY(cudaFuncSetAttribute(local_sort_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				      int(PACKED_SMEM)));
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.packed_blocks, local_sort_packed_kernel,
-							       LOCAL_THREADS, PACKED_SMEM));
+	CUDA_TRY(cudaFuncSetAttribute(MSB64_PACKED_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				      int(MSB64_PACKED_SMEM)));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.packed_blocks, MSB64_PACKED_KERNEL,
+							       LOCAL_THREADS, MSB64_PACKED_SMEM));
 	if (D.packed_blocks < 1) return fail(MSB64_ERR_CUDA, "packed local sort does not fit on an SM%s");
 	CUDA_TRY(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaMalloc(&D.scratch, 128 * sizeof(unsigned long long)));
@@ -288,9 +296,9 @@ Layout make_layout(uint64_t n)
 	Layout L;
 	const int maxbits = g_schedule_override.empty() ? 8 : MAX_BITS;
 	const uint64_t levels = MAX_LEVELS;
-	L.max_segs = uint32_t(n / LOCAL_CAP + 2);
+	L.max_segs = uint32_t(n / UNIT_CAP + 2);
 	L.max_tiles = uint32_t(n / TILE + 2 * uint64_t(L.max_segs) + 2);
-	L.max_units = uint32_t(2 * (n / LOCAL_CAP) + 2 * levels * L.max_segs + 16);
+	L.max_units = uint32_t(2 * (n / UNIT_CAP) + 2 * levels * L.max_segs + 16);
 	L.max_copies = uint32_t(n / COPY_TILE + L.max_segs + 2);
 	size_t at = 0;
 	auto take = [&](size_t bytes) { size_t o = at; at = align_up(at + bytes); return o; };
@@ -430,7 +438,7 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	if (tail) cudaEventRecord(tail[0], st);
 	// units whose keys leave room for a slot number in one word take the packed path, the rest
 	// (small arrays, very deep levels never) the general one; an empty list costs a launch
-	local_sort_packed_kernel<<<D.sms * D.packed_blocks, LOCAL_THREADS, PACKED_SMEM, st>>>(
+	MSB64_PACKED_KERNEL<<<D.sms * D.packed_blocks, LOCAL_THREADS, MSB64_PACKED_SMEM, st>>>(
 		c, rp.origin0 << rp.shift0);
 	local_sort_kernel<<<D.sms * D.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(
 		c, rp.origin0 << rp.shift0);

@@ -27,6 +27,9 @@ constexpr int MAX_BITS = 11;            // widest digit a level may use
 #define MSB64_LOCAL_CAP 4096
 #endif
 constexpr uint32_t LOCAL_CAP = MSB64_LOCAL_CAP;   // pairs the local sort holds in shared memory
+// Largest unit the plan kernel files: two slots short of LOCAL_CAP, so that a unit that begins at
+// an odd element still fits the local sort's 16-byte aligned window of LOCAL_CAP slots.
+constexpr uint32_t UNIT_CAP = LOCAL_CAP - 2;
 #ifndef MSB64_TILE
 #define MSB64_TILE 4096
 #endif
@@ -147,6 +150,10 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p)
 	uint64_t v;
 	asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
 	return v;
+}
+__device__ __forceinline__ void st_stream_u64x2(uint64_t *p, uint64_t a, uint64_t b)
+{
+	asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ void st_stream_u64(uint64_t *p, uint64_t v)
 {

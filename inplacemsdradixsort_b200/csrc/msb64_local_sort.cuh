@@ -202,7 +202,13 @@ local_sort_kernel(const Ctx c, const uint64_t base_key)
 		// them as 16-byte chunks of four at chunk indices c*OWNERS + t: the scan reads and
 		// writes them with conflict-free 16-byte accesses
 		constexpr int LPER = LOCAL_LPER, CH = LOCAL_CHUNKS;
+#ifdef MSB64_NATURAL_BINS
+#define MSB64_BIN_SLOT(d) (d)
+#define MSB64_BIN_CHUNK(ch, t) ((t) * CH + (ch))
+#else
 #define MSB64_BIN_SLOT(d) ((((((d) >> 2) & (CH - 1)) * OWNERS + ((d) >> LPER)) << 2) | ((d) & 3u))
+#define MSB64_BIN_CHUNK(ch, t) ((ch) * OWNERS + (t))
+#endif
 		// do the digit bits cover every differing bit?  then equal digit = equal key
 		const bool resolved = (diff & ((1ull << shift) - 1)) == 0;
 
@@ -232,7 +238,7 @@ local_sort_kernel(const Ctx c, const uint64_t base_key)
 #pragma unroll
 			for (int ch = 0; ch < CH; ++ch) {
 				uint4 v = make_uint4(0u, 0u, 0u, 0u);
-				if (own) v = b4[ch * OWNERS + tid];
+				if (own) v = b4[MSB64_BIN_CHUNK(ch, tid)];
 				cn[4 * ch] = v.x;
 				cn[4 * ch + 1] = v.y;
 				cn[4 * ch + 2] = v.z;
@@ -255,13 +261,13 @@ local_sort_kernel(const Ctx c, const uint64_t base_key)
 					base += cn[q];
 					if (!resolved && cn[q] >= 2u) {
 						if (cn[q] <= LOCAL_SERIAL_MAX) list[at++] = o;
-						else big[atomicAdd(&s_nbig, 1u)] = uint32_t((((q >> 2) * OWNERS + tid) << 2) | (q & 3));   // where the bin sits in the table
+						else big[atomicAdd(&s_nbig, 1u)] = uint32_t((MSB64_BIN_CHUNK(q >> 2, tid) << 2) | (q & 3));   // where the bin sits in the table
 					}
 					cn[q] = o;
 				}
 #pragma unroll
 				for (int ch = 0; ch < CH; ++ch)
-					b4[ch * OWNERS + tid] = make_uint4(cn[4 * ch], cn[4 * ch + 1], cn[4 * ch + 2], cn[4 * ch + 3]);
+					b4[MSB64_BIN_CHUNK(ch, tid)] = make_uint4(cn[4 * ch], cn[4 * ch + 1], cn[4 * ch + 2], cn[4 * ch + 3]);
 			}
 		}
 		__syncthreads();
@@ -390,6 +396,7 @@ local_sort_kernel(const Ctx c, const uint64_t base_key)
 			st_stream_u64(c.rids[0] + begin + i, srids[i]);
 		}
 #undef MSB64_BIN_SLOT
+#undef MSB64_BIN_CHUNK
 	}
 }
 

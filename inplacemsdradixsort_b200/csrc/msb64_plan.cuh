@@ -228,9 +228,9 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 			// buckets too large for shared memory: segments of the next level.  One pair of
 			// atomics claims segment and tile slots for all of the chunk's children (a
 			// round trip per child made the level-0 plan, one warp, the slowest step)
-			uint32_t large = __ballot_sync(0xffffffffu, cnt > LOCAL_CAP);
+			uint32_t large = __ballot_sync(0xffffffffu, cnt > UNIT_CAP);
 			if (large) {
-				const bool big = cnt > LOCAL_CAP;
+				const bool big = cnt > UNIT_CAP;
 				const uint32_t nt_mine = big ? seg_tile_count(beg, cnt) : 0u;
 				const uint32_t nt_inc = warp_inclusive_scan(nt_mine);
 				const uint32_t nt_all = __shfl_sync(0xffffffffu, nt_inc, 31);
@@ -273,11 +273,11 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 				present &= present - 1;
 				const uint32_t cb = __shfl_sync(0xffffffffu, cnt, src);
 				const uint32_t bb = __shfl_sync(0xffffffffu, beg, src);
-				if (cb > LOCAL_CAP || run_size + cb > LOCAL_CAP) {
+				if (cb > UNIT_CAP || run_size + cb > UNIT_CAP) {
 					if (run_size) add_unit(run_beg, run_size, run_dig);
 					local_pairs += run_size;
 					run_size = 0;
-					if (cb > LOCAL_CAP) continue;
+					if (cb > UNIT_CAP) continue;
 				}
 				if (run_size == 0) {
 					run_beg = bb;
