@@ -93,14 +93,21 @@ def parse_args():
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is under the bench's load.
+
+    The sampler is started in front of the warm-up steps (nvidia-smi needs a few hundred
+    milliseconds before its first sample, more than a short timed region lasts) and stopped
+    behind the timed region; mark() notes when the timed region begins, and the samples from
+    then on are the ones reported when there are any -- otherwise the samples of warm-up +
+    timed region together (same kernels, same load), which `window` says."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self):
         self.proc = None
         self.path = None
+        self.marked = None
 
     def start(self):
         try:
@@ -108,9 +115,20 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+
+    def mark(self):
+        self.marked = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self, gpu_index: int = 0) -> dict:
         if self.proc is None:
@@ -120,27 +138,31 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows, smax = [], None
         with open(self.path) as f:
             for line in f:
                 p = [x.strip() for x in line.split(",")]
-                if len(p) < 9 or not p[0].isdigit() or int(p[0]) != gpu_index:
+                if len(p) < 10 or not p[1].isdigit() or int(p[1]) != gpu_index:
                     continue
                 try:
-                    sm.append(float(p[1]))
-                    smax = float(p[2])
+                    mhz, smax = float(p[2]), float(p[3])
                 except ValueError:
                     continue
-                for name, val in zip(names, p[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
+                rows.append((self._stamp(p[0]), mhz,
+                             {n for n, v in zip(names, p[6:10]) if v.lower().startswith("active")}))
         os.unlink(self.path)
-        sm.sort()
-        # samples under load only (idle samples before/after would drag the median down)
-        loaded = [x for x in sm if smax and x > 0.5 * smax] or sm
-        med = loaded[len(loaded) // 2] if loaded else None
-        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        timed = [r for r in rows if self.marked and r[0] and r[0] >= self.marked - 0.02]
+        window = "timed region"
+        use = [r for r in timed if smax and r[1] > 0.5 * smax]
+        if len(use) < 3:
+            # too short a region for nvidia-smi's sampling: warm-up steps included
+            use = [r for r in rows if smax and r[1] > 0.5 * smax] or rows
+            window = "warm-up + timed region (the timed region alone gave fewer than 3 samples)"
+        sm = sorted(r[1] for r in use)
+        reasons = set().union(*[r[2] for r in use]) if use else set()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(use), "window": window}
 
 
 def measured_hbm_peak():
@@ -380,14 +402,14 @@ def main_b200(args):
         ok = bool(ok_all.item()) and wrap_sum(sum1) == wrap_sum(want_sum) and wrap_sum(dig1) == wrap_sum(want_dig)
         return ok and sorter.boundaries_ordered(out_k, out_n)
 
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 0)):
         restore()
         one_step()
     barrier()
-
-    sampler = ClockSampler()
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     launches0 = m.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]

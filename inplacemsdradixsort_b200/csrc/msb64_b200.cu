@@ -29,7 +29,6 @@
 #include "msb64_histogram.cuh"
 #include "msb64_local_sort.cuh"
 #include "msb64_local_packed.cuh"
-#include "msb64_local_packed2.cuh"
 #include "msb64_plan.cuh"
 #include "msb64_scatter.cuh"
 #include "msb64_route.cuh"
@@ -42,13 +41,6 @@ using namespace msb64;
 #endif
 #ifndef MSB64_SCATTER_MINB
 #define MSB64_SCATTER_MINB 3
-#endif
-#ifdef MSB64_PACKED_V1
-#define MSB64_PACKED_KERNEL local_sort_packed_kernel
-#define MSB64_PACKED_SMEM PACKED_SMEM
-#else
-#define MSB64_PACKED_KERNEL local_sort_packed2_kernel
-#define MSB64_PACKED_SMEM PACKED2_SMEM
 #endif
 constexpr int SCATTER_THREADS = MSB64_SCATTER_THREADS;
 constexpr int SCATTER_MINB = MSB64_SCATTER_MINB;
@@ -97,7 +89,9 @@ std::vector<int> make_schedule(uint64_t n, int width = 64)
 	int log_n = 0;
 	while (log_n < 63 && (2ull << log_n) <= n) ++log_n;                       // floor(log2 n)
 	if (log_n < 63 && double(n) > 1.41421356 * double(1ull << log_n)) ++log_n;
-	int need = log_n > 11 ? log_n - 11 : 0;
+	// half of the local sort's capacity: LOCAL_CAP = 4096 -> buckets of 2^11 pairs
+	constexpr int leaf_log = (LOCAL_CAP >= 4096 ? 12 : LOCAL_CAP >= 2048 ? 11 : 10) - 1;
+	int need = log_n > leaf_log ? log_n - leaf_log : 0;
 	if (need > width) need = width;
 	std::vector<int> s;
 	int used = 0;
@@ -243,10 +237,10 @@ int device_get(Device **out)
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.local_blocks, local_sort_kernel,
 							       LOCAL_THREADS, LOCAL_SMEM));
 	if (D.local_blocks < 1) return fail(MSB64_ERR_CUDA, "local sort does not fit on an SM%s");
-	CUDA_TRY(cudaFuncSetAttribute(MSB64_PACKED_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				      int(MSB64_PACKED_SMEM)));
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.packed_blocks, MSB64_PACKED_KERNEL,
-							       LOCAL_THREADS, MSB64_PACKED_SMEM));
+	CUDA_TRY(cudaFuncSetAttribute(local_sort_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+				      int(PACKED_SMEM)));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.packed_blocks, local_sort_packed_kernel,
+							       LOCAL_THREADS, PACKED_SMEM));
 	if (D.packed_blocks < 1) return fail(MSB64_ERR_CUDA, "packed local sort does not fit on an SM%s");
 	CUDA_TRY(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaMalloc(&D.scratch, 128 * sizeof(unsigned long long)));
@@ -438,7 +432,7 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	if (tail) cudaEventRecord(tail[0], st);
 	// units whose keys leave room for a slot number in one word take the packed path, the rest
 	// (small arrays, very deep levels never) the general one; an empty list costs a launch
-	MSB64_PACKED_KERNEL<<<D.sms * D.packed_blocks, LOCAL_THREADS, MSB64_PACKED_SMEM, st>>>(
+	local_sort_packed_kernel<<<D.sms * D.packed_blocks, LOCAL_THREADS, PACKED_SMEM, st>>>(
 		c, rp.origin0 << rp.shift0);
 	local_sort_kernel<<<D.sms * D.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(
 		c, rp.origin0 << rp.shift0);

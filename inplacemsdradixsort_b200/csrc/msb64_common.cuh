@@ -35,7 +35,10 @@ constexpr uint32_t UNIT_CAP = LOCAL_CAP - 2;
 #endif
 constexpr uint32_t TILE = MSB64_TILE;   // element slots per histogram/scatter tile
 constexpr uint32_t COPY_TILE = 8192;    // pairs per copy tile
-constexpr int FUSE_MAX_BITS = 13;       // level 0 + level 1 digit bits the fused histogram pass handles (32 KiB of counters)
+#ifndef MSB64_FUSE_MAX_BITS
+#define MSB64_FUSE_MAX_BITS 13
+#endif
+constexpr int FUSE_MAX_BITS = MSB64_FUSE_MAX_BITS;   // level 0 + level 1 digit bits the fused histogram pass handles (4 << bits bytes of shared counters)
 
 struct Seg {
 	uint32_t begin;   // first element

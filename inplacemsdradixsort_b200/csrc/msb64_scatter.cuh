@@ -42,7 +42,7 @@ struct ScatterCfg {
 				       + size_t(NB) * 4                // delta
 				       + 64 * 4                        // scan scratch
 				       + 3 * 32                        // tile descriptors, three deep
-				       + 16;                           // mbarrier
+				       + 16;                           // two mbarriers (keys, rids)
 };
 
 // What a block needs to know about one tile (kept in shared memory, written by thread 0).
@@ -164,34 +164,44 @@ scatter_kernel(const Ctx c, const int level, const uint32_t origin)
 		const uint32_t w = min(uint32_t(TILE), (end - lo + 1u) & ~1u);
 		return lo + w <= c.end ? w : 0u;
 	};
-	// thread 0 only (slots in front of the segment receive the neighbours' data and are ignored)
-	auto start_copy = [&](const TileDesc &d) {
+	// thread 0 only (slots in front of the segment receive the neighbours' data and are ignored).
+	// Keys and rids travel separately, each behind its own mbarrier: the keys' buffer is free
+	// as soon as the keys have been written out, the rids are not needed before the write-out.
+	auto start_keys = [&](const TileDesc &d) {
 		if (d.flags & (TD_SKIP | TD_NONE)) return;
 		const uint32_t w = window(d.lo, d.end);
 		if (!w) return;
-		const bool b = d.flags & TD_BUF;
-		mbar_expect_tx(bar, w * 16);
-		bulk_copy_g2s(kin, (b ? c.keys[1] : c.keys[0]) + d.lo, w * 8, bar);
-		bulk_copy_g2s(rin, (b ? c.rids[1] : c.rids[0]) + d.lo, w * 8, bar);
+		mbar_expect_tx(&bar[0], w * 8);
+		bulk_copy_g2s(kin, ((d.flags & TD_BUF) ? c.keys[1] : c.keys[0]) + d.lo, w * 8, &bar[0]);
+	};
+	auto start_rids = [&](const TileDesc &d) {
+		if (d.flags & (TD_SKIP | TD_NONE)) return;
+		const uint32_t w = window(d.lo, d.end);
+		if (!w) return;
+		mbar_expect_tx(&bar[1], w * 8);
+		bulk_copy_g2s(rin, ((d.flags & TD_BUF) ? c.rids[1] : c.rids[0]) + d.lo, w * 8, &bar[1]);
 	};
 
 	if (tid == 0) {
-		mbar_init(bar, 1);
+		mbar_init(&bar[0], 1);
+		mbar_init(&bar[1], 1);
 		fetch_desc(blockIdx.x, &sdesc[0]);
 		fetch_desc(blockIdx.x + G, &sdesc[1]);
-		start_copy(sdesc[0]);
+		start_keys(sdesc[0]);
+		start_rids(sdesc[0]);
 	}
 	for (int i = tid; i < NB + 32; i += THREADS) cnt[i] = 0;
 	__syncthreads();
 
-	uint32_t parity = 0, slot = 0;
+	uint32_t parity_k = 0, parity_r = 0, slot = 0;
 	for (uint32_t t = blockIdx.x; t < ntiles; t += G, slot = slot == 2 ? 0 : slot + 1) {
 		const TileDesc cur = sdesc[slot];
 		TileDesc *next_slot = &sdesc[slot == 2 ? 0 : slot + 1];
 		TileDesc *after_slot = &sdesc[slot == 0 ? 2 : slot - 1];       // slot + 2 mod 3
 		if (cur.flags & TD_SKIP) {
 			if (tid == 0) {
-				start_copy(*next_slot);
+				start_keys(*next_slot);
+				start_rids(*next_slot);
 				fetch_desc(t + 2 * G, after_slot);
 			}
 			__syncthreads();
@@ -205,10 +215,11 @@ scatter_kernel(const Ctx c, const int level, const uint32_t origin)
 		const bool full = lo >= cur.begin && lo + TILE <= cur.end;
 		const uint32_t count = min(lo + TILE, cur.end) - max(lo, cur.begin);
 
-		// 0. the tile's pairs in shared memory
-		if (window(lo, cur.end)) {
-			mbar_wait(bar, parity);
-			parity ^= 1u;
+		// 0. the tile's keys in shared memory (the rids are awaited in front of their write-out)
+		const bool bulk = window(lo, cur.end) != 0;
+		if (bulk) {
+			mbar_wait(&bar[0], parity_k);
+			parity_k ^= 1u;
 		} else {
 			// the window would cross the end of the array (last tile only): plain loads
 			const uint64_t *src_keys = src_b ? c.keys[1] : c.keys[0];
@@ -276,23 +287,37 @@ scatter_kernel(const Ctx c, const int level, const uint32_t origin)
 		}
 		__syncthreads();
 
-		// 4. coalesced write-out: position i of the bin-ordered tile goes to delta[bin] + i
-#pragma unroll 8
-		for (uint32_t i = tid; i < count; i += THREADS) {
-			const uint32_t s = sidx[i];
-			const uint64_t key = kin[s];
-			const uint64_t rid = rin[s];
-			const uint32_t dst = delta[(uint32_t(key >> shift) - origin) & (NB - 1)] + i;
-			st_stream_u64(dst_keys + dst, key);
-			st_stream_u64(dst_rids + dst, rid);
+		// 4. coalesced write-out: position i of the bin-ordered tile goes to delta[bin] + i.
+		//    Keys first; once every thread has read its keys the keys of the NEXT tile are
+		//    requested into the same buffer (they land while the rids go out and the
+		//    counters are cleared), then the rids, then the next tile's rids are requested
+		//    (they land while the next tile is being ranked).
+		uint32_t dst[ITEMS];
+#pragma unroll
+		for (int j = 0; j < ITEMS; ++j) {
+			const uint32_t i = j * THREADS + tid;
+			if (i < count) {
+				const uint64_t key = kin[sidx[i]];
+				dst[j] = delta[(uint32_t(key >> shift) - origin) & (NB - 1)] + i;
+				st_stream_u64(dst_keys + dst[j], key);
+			}
+		}
+		__syncthreads();
+		if (tid == 0) start_keys(*next_slot);
+		if (bulk) {
+			mbar_wait(&bar[1], parity_r);
+			parity_r ^= 1u;
+		}
+#pragma unroll
+		for (int j = 0; j < ITEMS; ++j) {
+			const uint32_t i = j * THREADS + tid;
+			if (i < count) st_stream_u64(dst_rids + dst[j], rin[sidx[i]]);
 		}
 		// meanwhile: counters back to zero for the next tile, descriptor of the tile after it
 		for (int i = tid; i < NB + 32; i += THREADS) cnt[i] = 0;
 		if (tid == 0) fetch_desc(t + 2 * G, after_slot);
 		__syncthreads();
-		// the tile's buffers are free: request the next tile (the other blocks on this SM
-		// cover the latency)
-		if (tid == 0) start_copy(*next_slot);
+		if (tid == 0) start_rids(*next_slot);
 	}
 }
 

@@ -5,10 +5,11 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import inplacemsdradixsort_b200 as m
+from bench import parse_count
 
-n = int(eval(sys.argv[1])) if len(sys.argv) > 1 else 1 << 26
+n = parse_count(sys.argv[1]) if len(sys.argv) > 1 else 1 << 26
 kind = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-param = int(eval(sys.argv[3])) if len(sys.argv) > 3 else 0
+param = parse_count(sys.argv[3]) if len(sys.argv) > 3 else 0
 sched = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else None
 if sched:
     m.set_schedule(sched)
@@ -26,5 +27,6 @@ for it in range(4):
     print(it, ph, "total_us", tot, "Gpairs/s %.2f" % (n / tot / 1e3))
 bad, s1, d1 = dk.check(dr)
 print("n", n, "kind", kind, "sched", m.get_schedule(n), "bad", bad, "sum_ok", s0 == s1, "digest_ok", d0 == d1)
+print("levels(us)", [(l["histogram"], l["plan"], l["scatter"]) for l in m.last_level_times()][:6])
 print("stats", m.last_stats())
 print("best Gpairs/s %.2f" % (n / best / 1e3))

@@ -9,7 +9,8 @@ import torch
 
 import inplacemsdradixsort_b200 as m
 
-n = int(eval(sys.argv[1])) if len(sys.argv) > 1 else 1 << 28
+from bench import parse_count
+n = parse_count(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
 lib = m.load_library()
 dev = torch.device("cuda", 0)
 k = torch.empty(n, dtype=torch.int64, device=dev)
