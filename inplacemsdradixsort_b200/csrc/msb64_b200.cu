@@ -73,6 +73,17 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------ schedule
 std::vector<int> g_schedule_override;
 const bool g_no_fuse = getenv("MSB64_NO_FUSE") != nullptr;     // developer switch: separate histogram pass per level
+const bool g_debug_sync = getenv("MSB64_DEBUG_SYNC") != nullptr;   // developer switch: synchronise behind every kernel, name the one that faults
+
+void debug_sync(cudaStream_t st, const char *what, int level = -1)
+{
+	if (!g_debug_sync) return;
+	const cudaError_t e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) {
+		fprintf(stderr, "msb64 debug: %s (level %d): %s\n", what, level, cudaGetErrorString(e));
+		abort();
+	}
+}
 
 // Digit widths, most significant first (the role of schedule_passes, msb_64.c:1334), for
 // keys of which only the low `width` bits vary (64 when nothing is known about the keys).
@@ -330,10 +341,13 @@ void launch_level(Device &D, const Ctx &c, int level, int shift0, uint32_t origi
 		histogram_kernel<BITS, 256, false><<<D.sms * D.hist_blocks[BITS], 256, H::SMEM, st>>>(
 			c, level, origin, 0);
 	}
+	debug_sync(st, "histogram_kernel", level);
 	if (ev) cudaEventRecord(ev[1], st);
 	plan_kernel<<<D.sms * 4, PLAN_THREADS, 0, st>>>(c, level, BITS, next_bits, fuse);
+	debug_sync(st, "plan_kernel", level);
 	if (ev) cudaEventRecord(ev[2], st);
 	scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB><<<D.sms * D.scatter_blocks[BITS], SCATTER_THREADS, S::SMEM, st>>>(c, level, origin);
+	debug_sync(st, "scatter_kernel", level);
 	if (ev) cudaEventRecord(ev[3], st);
 	g_launches += 3;
 }
@@ -405,6 +419,7 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	const int levels = int(sched.size());
 	if (ev) cudaEventRecord(ev[0], st);
 	init_kernel<<<D.sms, 256, 0, st>>>(c, sched[0], rp.shift0);
+	debug_sync(st, "init_kernel");
 	g_launches += 1;
 	if (n > LOCAL_CAP) {
 		// the position of a segment's digit travels with the segment (msb64_plan.cuh); the
@@ -434,11 +449,14 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 	// (small arrays, very deep levels never) the general one; an empty list costs a launch
 	local_sort_packed_kernel<<<D.sms * D.packed_blocks, LOCAL_THREADS, PACKED_SMEM, st>>>(
 		c, rp.origin0 << rp.shift0);
+	debug_sync(st, "local_sort_packed_kernel");
 	local_sort_kernel<<<D.sms * D.local_blocks, LOCAL_THREADS, LOCAL_SMEM, st>>>(
 		c, rp.origin0 << rp.shift0);
+	debug_sync(st, "local_sort_kernel");
 	g_launches += 1;
 	if (tail) cudaEventRecord(tail[1], st);
 	copy_kernel<<<D.sms * 8, 256, 0, st>>>(c);
+	debug_sync(st, "copy_kernel");
 	if (tail) cudaEventRecord(tail[2], st);
 	g_launches += 2;
 	CUDA_TRY(cudaGetLastError());

@@ -84,7 +84,10 @@ __global__ void __launch_bounds__(LOCAL_THREADS, LOCAL_MINB)
 local_sort_packed_kernel(const Ctx c, const uint64_t base_key)
 {
 	constexpr int THREADS = LOCAL_THREADS, CH = PACK_CHUNKS, WARPS = THREADS / 32, PER = PACK_PER;
-	constexpr uint32_t SLOT_MASK = (1u << PACK_SLOT_BITS) - 1;
+	// slots are window indices < LOCAL_CAP; the mask also keeps the index read from a window
+	// position outside the unit (stale bits, never stored) inside the rid window
+	static_assert((LOCAL_CAP & (LOCAL_CAP - 1)) == 0, "slot mask");
+	constexpr uint32_t SLOT_MASK = LOCAL_CAP - 1;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint64_t *pk = reinterpret_cast<uint64_t *>(smem_raw);            // [LOCAL_CAP] packed words
 	uint64_t *rin = pk + LOCAL_CAP;                                   // [LOCAL_CAP] rids of the window
