@@ -114,12 +114,15 @@ int msb64_b200_sort_device_range(uint64_t *d_keys, uint64_t *d_rids, uint64_t n,
 #define MSB64_PHASE_SCATTER   2	/* partition kernels                  (msb_64.c:740-978)  */
 #define MSB64_PHASE_LOCAL     3	/* small-bucket finish in shared mem  (msb_64.c:126-149, 980-1005) */
 #define MSB64_PHASE_COPY      4	/* buckets finished in the scratch buffer copied home */
-#define MSB64_PHASE_COUNT     5
+#define MSB64_PHASE_TAIL      5	/* histogram + plan + scatter of the levels below the depth uniform
+				   keys need, one cooperative launch (skewed inputs only; msb_64.c:1007-1035) */
+#define MSB64_PHASE_COUNT     6
 
-/* Digit schedule: widths of the MSD digits, most significant first, summing to
- * 64 (the role of schedule_passes, msb_64.c:1334-1400).  Returns the number of
- * levels written to bits[] (<= 16).  msb64_b200_set_schedule overrides the
- * default choice for later calls (count = 0 restores the default). */
+/* Digit schedule: widths of the MSD digits, most significant first, covering all 64
+ * bits (the role of schedule_passes, msb_64.c:1334-1400): they sum to at least 64, the
+ * last digit starts above bit 0 and is clamped there.  Returns the number of levels
+ * written to bits[] (<= 16).  msb64_b200_set_schedule overrides the default choice for
+ * later calls with widths that sum to exactly 64 (count = 0 restores the default). */
 int msb64_b200_get_schedule(uint64_t n, int *bits);
 int msb64_b200_set_schedule(const int *bits, int count);
 /* The schedule msb64_b200_sort_device_range uses for keys in [key_lo, key_hi]: digit widths

@@ -32,6 +32,7 @@
 #include "msb64_plan.cuh"
 #include "msb64_scatter.cuh"
 #include "msb64_route.cuh"
+#include "msb64_tail.cuh"
 
 using namespace msb64;
 
@@ -73,6 +74,7 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------ schedule
 std::vector<int> g_schedule_override;
 const bool g_no_fuse = getenv("MSB64_NO_FUSE") != nullptr;     // developer switch: separate histogram pass per level
+const int g_tail_from = getenv("MSB64_TAIL_FROM") ? atoi(getenv("MSB64_TAIL_FROM")) : 0;   // developer switch: levels from here on run in the tail kernel (they must be 7 bits wide)
 const bool g_debug_sync = getenv("MSB64_DEBUG_SYNC") != nullptr;   // developer switch: synchronise behind every kernel, name the one that faults
 
 void debug_sync(cudaStream_t st, const char *what, int level = -1)
@@ -87,9 +89,14 @@ void debug_sync(cudaStream_t st, const char *what, int level = -1)
 
 // Digit widths, most significant first (the role of schedule_passes, msb_64.c:1334), for
 // keys of which only the low `width` bits vary (64 when nothing is known about the keys).
-std::vector<int> make_schedule(uint64_t n, int width = 64)
+// *head (optional): the number of leading levels uniform keys need; the levels after them (the
+// "tail") are TAIL_BITS wide each and run inside one cooperative launch (msb64_tail.cuh).
+std::vector<int> make_schedule(uint64_t n, int width = 64, int *head = nullptr)
 {
-	if (width == 64 && !g_schedule_override.empty()) return g_schedule_override;
+	if (width == 64 && !g_schedule_override.empty()) {
+		if (head) *head = int(g_schedule_override.size());     // an override runs level by level
+		return g_schedule_override;
+	}
 	// Uniform keys stop descending once the average bucket fits the local sort with
 	// room to spare (2048 pairs): that takes `need` bits.  The scatter's HBM efficiency
 	// falls with the run length TILE / 2^bits (tools/permcopy.cu: 6.3 TB/s at 256-byte
@@ -115,17 +122,17 @@ std::vector<int> make_schedule(uint64_t n, int width = 64)
 			used += b;
 		}
 	}
-	// the rest of the key (only skewed inputs get here): 7-bit digits, 4..7 bits at the end.
-	// Dead digits cost next to nothing (the plan kernel moves a segment down to its highest
+	// the rest of the key (only skewed inputs get here): 7-bit digits down to bit 0.  Dead
+	// digits cost next to nothing (the plan kernel moves a segment down to its highest
 	// differing bit), so the digits that do get used should be narrow enough for full-speed
-	// scatter passes.  The last digit may reach above `width` (those bits are equal in every key).
-	int rest = width - used;
-	while (rest > 0) {
-		int b = rest <= 7 ? (rest < 4 ? 4 : rest) : (rest < 11 ? rest - rest / 2 : 7);
-		s.push_back(b);
-		rest -= b;
+	// scatter passes.  The last digit may reach below bit 0 / above `width`: a digit's position
+	// is clamped at bit 0 and its surplus high bits were consumed by the level above.
+	if (s.empty()) {
+		s.push_back(TAIL_BITS);
+		used += TAIL_BITS;
 	}
-	if (s.empty()) s.push_back(4);
+	if (head) *head = int(s.size());
+	for (int rest = width - used; rest > 0; rest -= TAIL_BITS) s.push_back(TAIL_BITS);
 	return s;
 }
 
@@ -134,6 +141,7 @@ std::vector<int> make_schedule(uint64_t n, int width = 64)
 // digits below level 0 are plain bit fields under shift0.
 struct RangePlan {
 	std::vector<int> sched;
+	int head;               // levels [head, sched.size()) are the tail (make_schedule)
 	int shift0;
 	uint64_t origin0;       // lo >> shift0
 };
@@ -147,7 +155,7 @@ RangePlan plan_range(uint64_t n, uint64_t lo, uint64_t hi)
 	while (width < 64 && (span >> width)) ++width;
 	if (width < 1) width = 1;
 	for (;; ++width) {
-		r.sched = make_schedule(n, width);
+		r.sched = make_schedule(n, width, &r.head);
 		const int bits0 = r.sched[0];
 		r.shift0 = width > bits0 ? width - bits0 : 0;
 		r.origin0 = lo >> r.shift0;
@@ -169,7 +177,7 @@ struct Device {
 	int hist_blocks[MAX_BITS + 1] = {0};      // resident blocks per SM, by digit width
 	int fused_blocks[MAX_BITS + 1] = {0};     // same for the fused (two-level) histogram
 	int scatter_blocks[MAX_BITS + 1] = {0};
-	int local_blocks = 0, packed_blocks = 0;
+	int local_blocks = 0, packed_blocks = 0, tail_blocks = 0;
 	bool route_configured = false;
 	// cached allocations (grow-only)
 	void *ws = nullptr;
@@ -253,6 +261,11 @@ int device_get(Device **out)
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.packed_blocks, local_sort_packed_kernel,
 							       LOCAL_THREADS, PACKED_SMEM));
 	if (D.packed_blocks < 1) return fail(MSB64_ERR_CUDA, "packed local sort does not fit on an SM%s");
+	CUDA_TRY(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tail_smem())));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&D.tail_blocks, tail_kernel, TAIL_THREADS, tail_smem()));
+	int coop = 0;
+	CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+	if (D.tail_blocks < 1 || !coop) return fail(MSB64_ERR_CUDA, "tail kernel: no cooperative launch / does not fit on an SM%s");
 	CUDA_TRY(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaMalloc(&D.scratch, 128 * sizeof(unsigned long long)));
 	CUDA_TRY(cudaHostAlloc(&D.status_h, sizeof(uint32_t), cudaHostAllocMapped));
@@ -417,14 +430,23 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 		ev = D.ev;
 	}
 	const int levels = int(sched.size());
+	// levels [0, head) one by one, levels [head, levels) -- all TAIL_BITS wide, reached by skewed
+	// inputs only -- inside one cooperative launch that leaves at the first empty level
+	int head = std::min(std::max(rp.head, 1), levels);
+	if (g_tail_from > 0 && g_tail_from < levels) {
+		head = g_tail_from;
+		for (int l = head; l < levels; ++l)
+			if (sched[l] != TAIL_BITS) return fail(MSB64_ERR_ARG, "MSB64_TAIL_FROM: tail digits must be 7 bits wide%s");
+	}
 	if (ev) cudaEventRecord(ev[0], st);
 	init_kernel<<<D.sms, 256, 0, st>>>(c, sched[0], rp.shift0);
 	debug_sync(st, "init_kernel");
 	g_launches += 1;
+	cudaEvent_t *tail = ev ? ev + 1 + 4 * head : nullptr;
 	if (n > LOCAL_CAP) {
 		// the position of a segment's digit travels with the segment (msb64_plan.cuh); the
 		// host only says where level 0 starts
-		for (int l = 0; l < levels; ++l) {
+		for (int l = 0; l < head; ++l) {
 			const int bits = sched[l];
 			const int shift = rp.shift0;
 			const uint32_t origin = l == 0 ? uint32_t(rp.origin0) : 0u;
@@ -442,9 +464,20 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 			default: return fail(MSB64_ERR_ARG, "digit width outside 4..11%s");
 			}
 		}
+		if (tail) cudaEventRecord(tail[0], st);
+		if (head < levels) {
+			Ctx cc = c;
+			int first = head, last = levels - 1;
+			void *args[] = {&cc, &first, &last};
+			CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(tail_kernel), dim3(D.sms * D.tail_blocks),
+							     dim3(TAIL_THREADS), args, tail_smem(), st));
+			debug_sync(st, "tail_kernel");
+			g_launches += 1;
+		}
+	} else if (tail) {
+		cudaEventRecord(tail[0], st);
 	}
-	cudaEvent_t *tail = ev ? ev + 1 + 4 * levels : nullptr;
-	if (tail) cudaEventRecord(tail[0], st);
+	if (tail) cudaEventRecord(tail[1], st);
 	// units whose keys leave room for a slot number in one word take the packed path, the rest
 	// (small arrays, very deep levels never) the general one; an empty list costs a launch
 	local_sort_packed_kernel<<<D.sms * D.packed_blocks, LOCAL_THREADS, PACKED_SMEM, st>>>(
@@ -454,10 +487,10 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 		c, rp.origin0 << rp.shift0);
 	debug_sync(st, "local_sort_kernel");
 	g_launches += 1;
-	if (tail) cudaEventRecord(tail[1], st);
+	if (tail) cudaEventRecord(tail[2], st);
 	copy_kernel<<<D.sms * 8, 256, 0, st>>>(c);
 	debug_sync(st, "copy_kernel");
-	if (tail) cudaEventRecord(tail[2], st);
+	if (tail) cudaEventRecord(tail[3], st);
 	g_launches += 2;
 	CUDA_TRY(cudaGetLastError());
 	D.last_ctl = c.ctl;
@@ -472,7 +505,7 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 		};
 		phase_us[MSB64_PHASE_PLAN] += us(ev[0], ev[1]);
 		if (n > LOCAL_CAP)
-			for (int l = 0; l < levels; ++l) {
+			for (int l = 0; l < head; ++l) {
 				cudaEvent_t *lev = ev + 1 + 4 * l;
 				D.level_us[l][0] = us(lev[0], lev[1]);
 				D.level_us[l][1] = us(lev[1], lev[2]);
@@ -481,9 +514,10 @@ int sort_device_locked(uint64_t *d_keys, uint64_t *d_rids, uint64_t n, void *wor
 				phase_us[MSB64_PHASE_PLAN] += D.level_us[l][1];
 				phase_us[MSB64_PHASE_SCATTER] += D.level_us[l][2];
 			}
-		D.last_levels = n > LOCAL_CAP ? levels : 0;
-		phase_us[MSB64_PHASE_LOCAL] = us(tail[0], tail[1]);
-		phase_us[MSB64_PHASE_COPY] = us(tail[1], tail[2]);
+		D.last_levels = n > LOCAL_CAP ? head : 0;
+		phase_us[MSB64_PHASE_TAIL] = us(tail[0], tail[1]);
+		phase_us[MSB64_PHASE_LOCAL] = us(tail[1], tail[2]);
+		phase_us[MSB64_PHASE_COPY] = us(tail[2], tail[3]);
 		if (take_status(D)) return fail(MSB64_ERR_INTERNAL, "device work list overflow%s");
 	}
 	return MSB64_OK;
@@ -616,7 +650,7 @@ int digit_histogram_locked(const uint64_t *d_keys, uint64_t n, int shift, int bi
 const char *kPhaseNames[] = {
 	"Copy to device time:      ", "Histogram time:           ", "Plan time:                ",
 	"Scatter time:             ", "Local sort time:          ", "Copy home time:           ",
-	"Copy to host time:        ",
+	"Tail levels time:         ", "Copy to host time:        ",
 };
 
 int sort_host_locked(uint64_t **keys, uint64_t **rids, uint64_t *size, int numa, double fudge,

@@ -169,6 +169,43 @@ __device__ __forceinline__ void st_stream_u64(uint64_t *p, uint64_t v)
 #endif
 }
 
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t *bar)
+{
+	asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		     :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+			     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			     "selp.u32 %0, 1, 0, p;\n\t}"
+			     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+	} while (!done);
+}
+// bytes: multiple of 16; dst and src 16-byte aligned
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		     :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
 // Inclusive-to-exclusive block scan helper over one value per thread.
 // scratch: THREADS/32 + 1 words of shared memory.  Returns the exclusive prefix;
 // *total receives the block sum.  Contains two __syncthreads().

@@ -129,9 +129,19 @@ __device__ __forceinline__ void emit_copy(const Ctx &c, Control *ctl, uint32_t b
 //     however many bits further down that is.
 // Presorted, low-entropy and duplicate-heavy inputs pay two histogram passes for a run of
 // dead digits, not one per digit; inputs without degenerate digits pay nothing.
-__global__ void __launch_bounds__(PLAN_THREADS)
-plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, const bool fused)
+//
+// A level that holds a single segment (level 0 always; the first level of every sub-range sort
+// of the sharded path) would leave the whole job -- up to 2^bits children, each with a
+// histogram row to copy and a tile list to write -- to one warp.  There the warp only claims the
+// children's slots and notes them in shared memory; the block's other warps then write the rows
+// and tile lists with it (a level-0 plan of 128 children x 2048 tiles: 229 -> ~50 us).
+// notes: PLAN_NOTES words of shared memory (the caller's: static in plan_kernel, a corner of the
+// dynamic allocation in the tail kernel).
+constexpr uint32_t PLAN_NOTES = 3u << MAX_BITS;
+__device__ __forceinline__ void plan_pass(const Ctx &c, const int level, const int bits, const int next_bits,
+					   const bool fused, uint32_t *notes)
 {
+	uint32_t *d_child = notes, *d_tile = notes + (1u << MAX_BITS), *d_nt = notes + (2u << MAX_BITS);
 	const uint32_t lane = lane_id();
 	const uint32_t warps_per_block = PLAN_THREADS / 32;
 	const uint32_t NB = 1u << bits, NBN = next_bits ? (1u << next_bits) : 0u;
@@ -143,6 +153,12 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 	uint32_t *hist_out = (level & 1) ? c.hist[0] : c.hist[1];
 	const SegBits *segbits = (level & 1) ? c.segbits[1] : c.segbits[0];
 	const uint32_t nsegs = min(ctl->nsegs[level], c.max_segs);
+	const bool single = nsegs == 1;              // the same on every thread of the grid
+	if (single) {
+		if (blockIdx.x != 0) return;
+		for (uint32_t b = threadIdx.x; b < NB; b += PLAN_THREADS) d_child[b] = 0xffffffffu;
+		__syncthreads();
+	}
 
 	for (uint32_t sg = blockIdx.x * warps_per_block + (threadIdx.x >> 5); sg < nsegs;
 	     sg += gridDim.x * warps_per_block) {
@@ -254,6 +270,15 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 						segs_out[my_child] = Seg{beg, cnt, dst_buf, seg_flags(child_shift, fused ? SEG_HIST_READY : 0u)};
 						((level & 1) ? c.segbits[0] : c.segbits[1])[my_child] = SegBits{0ull, ~0ull};
 					}
+					if (single) {
+						// rows and tile lists: by the whole block, after the loop
+						if (big) {
+							d_child[b] = my_child;
+							d_tile[b] = my_tile;
+							d_nt[b] = nt_mine;
+						}
+						large = 0;
+					}
 					while (large) {
 						const int src = __ffs(large) - 1;
 						large &= large - 1;
@@ -295,6 +320,24 @@ plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, c
 			emit_copy(c, ctl, s.begin, s.size);           // final data ends in the scratch buffer
 		}
 	}
+	if (single) {
+		__syncthreads();
+		for (uint32_t b = threadIdx.x >> 5; b < NB; b += warps_per_block) {
+			const uint32_t child = d_child[b];
+			if (child == 0xffffffffu) continue;
+			const uint32_t tile_at = d_tile[b], nt = d_nt[b];
+			const uint32_t *row = fused ? c.fused + size_t(b) * NBN : nullptr;
+			for (uint32_t j = lane; j < NBN; j += 32) hist_out[size_t(child) * NBN + j] = row ? row[j] : 0u;
+			for (uint32_t j = lane; j < nt; j += 32) tiles_out[tile_at + j] = Tile{child, j};
+		}
+	}
+}
+
+__global__ void __launch_bounds__(PLAN_THREADS)
+plan_kernel(const Ctx c, const int level, const int bits, const int next_bits, const bool fused)
+{
+	__shared__ uint32_t notes[PLAN_NOTES];
+	plan_pass(c, level, bits, next_bits, fused, notes);
 }
 
 // Buckets that are final but sit in B (all-equal keys after the last digit).

@@ -57,39 +57,6 @@ struct TileDesc {
 };
 constexpr uint32_t TD_BUF = 1u, TD_SKIP = 2u, TD_NONE = 4u;
 
-// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
-__device__ __forceinline__ uint32_t smem_addr(const void *p)
-{
-	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-		     :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-	uint32_t done;
-	do {
-		asm volatile("{\n\t.reg .pred p;\n\t"
-			     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-			     "selp.u32 %0, 1, 0, p;\n\t}"
-			     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-	} while (!done);
-}
-// bytes: multiple of 16; dst and src 16-byte aligned
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		     :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-
 // Rank of a key among the tile's keys with the same digit = old value of the tile's
 // bin counter.  The hot loop is branch-free on purpose: ptxas re-materialises the
 // shared-window base (S2UR SR_CgaCtaId) in front of every ATOMS that sits behind a
@@ -116,9 +83,10 @@ __device__ __forceinline__ void tile_ranks(uint32_t *cnt, uint32_t (&d)[ITEMS])
 	}
 }
 
-template <int BITS, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-scatter_kernel(const Ctx c, const int level, const uint32_t origin)
+// (the pass as a device function: scatter_kernel below and the cooperative tail kernel,
+// msb64_tail.cuh, run the same code)
+template <int BITS, int THREADS>
+__device__ __forceinline__ void scatter_pass(const Ctx &c, const int level, const uint32_t origin)
 {
 	using Cfg = ScatterCfg<BITS, THREADS>;
 	constexpr int NB = Cfg::NB, ITEMS = Cfg::ITEMS, BPT = Cfg::BPT;
@@ -319,6 +287,19 @@ scatter_kernel(const Ctx c, const int level, const uint32_t origin)
 		__syncthreads();
 		if (tid == 0) start_rids(*next_slot);
 	}
+	// nothing is in flight (a tile's copies are awaited before the next ones are requested):
+	// give the barriers' words back, the tail kernel runs other passes in this memory
+	if (tid == 0) {
+		mbar_inval(&bar[0]);
+		mbar_inval(&bar[1]);
+	}
+}
+
+template <int BITS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+scatter_kernel(const Ctx c, const int level, const uint32_t origin)
+{
+	scatter_pass<BITS, THREADS>(c, level, origin);
 }
 
 } // namespace msb64

@@ -26,7 +26,7 @@ _u64pp = C.POINTER(_u64p)
 MSB64_OK = 0
 MSB64_MAX_PAIRS = 0xFFFF0000
 MSB64_SHARD_HANDLE_BYTES = 192
-PHASES = ("histogram", "plan", "scatter", "local_sort", "copy_home")
+PHASES = ("histogram", "plan", "scatter", "local_sort", "copy_home", "tail")
 ERRORS = {-1: "CUDA", -2: "ARG", -3: "TOO_BIG", -4: "CAPACITY", -5: "NOMEM", -6: "INTERNAL"}
 
 # every symbol include/msb64_b200.h declares (checked by tests without a GPU)
