@@ -489,7 +489,7 @@ def main_b200(args):
                 "frac_of_nvlink": gbs / 900.0 if gbs else None,
                 "note": "max over ranks, one timed step; plan = histogram + all-gather + host cut; route = local "
                         "bucket pass; exchange = first to last outgoing copy (copy engines, NVLink); first_wait = "
-                        "main stream idle until sub-range 0 is complete; sort = 16 sub-range sorts, running "
+                        "main stream idle until sub-range 0 is complete; sort = the sub-range sorts (32 per GPU up to 4 GPUs, 16 on 8), running "
                         "while the later sub-ranges are still travelling (exchange_hidden_ms of the exchange)",
             }
         else:

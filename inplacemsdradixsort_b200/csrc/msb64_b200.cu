@@ -175,7 +175,7 @@ struct Device {
 	int index = -1;
 	int sms = 0;
 	int hist_blocks[MAX_BITS + 1] = {0};      // resident blocks per SM, by digit width
-	int fused_blocks[MAX_BITS + 1] = {0};     // same for the fused (two-level) histogram
+	int fused_blocks[MAX_BITS + 1][FUSE_MAX_BITS + 1] = {{0}};   // same for the fused (two-level) histogram, by both widths
 	int scatter_blocks[MAX_BITS + 1] = {0};
 	int local_blocks = 0, packed_blocks = 0, tail_blocks = 0;
 	bool route_configured = false;
@@ -211,9 +211,11 @@ int setup_bits(Device &D)
 		CUDA_TRY(cudaFuncSetAttribute(histogram_kernel<BITS, 256, true>,
 					      cudaFuncAttributeMaxDynamicSharedMemorySize,
 					      int(H::SMEM + (size_t(H::NB + 32) << (FUSE_MAX_BITS - BITS)) * 4)));
-		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-			&D.fused_blocks[BITS], histogram_kernel<BITS, 256, true>, 256,
-			H::SMEM + (size_t(H::NB + 32) << (FUSE_MAX_BITS - BITS)) * 4));
+		// the table of level-1 counts grows with the level-1 width: so does the block's footprint
+		for (int fb = 4; BITS + fb <= FUSE_MAX_BITS; ++fb)
+			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+				&D.fused_blocks[BITS][fb], histogram_kernel<BITS, 256, true>, 256,
+				H::SMEM + (size_t(H::NB + 32) << fb) * 4));
 	}
 	CUDA_TRY(cudaFuncSetAttribute(scatter_kernel<BITS, SCATTER_THREADS, SCATTER_MINB>,
 				      cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::SMEM)));
@@ -345,10 +347,10 @@ void launch_level(Device &D, const Ctx &c, int level, int shift0, uint32_t origi
 	// level 0 is one segment: its histogram pass also counts the level-1 digits per bin
 	// (32 KiB of shared counters), and level 1 needs no histogram pass
 	const bool fuse = level == 0 && next_bits > 0 && BITS + next_bits <= FUSE_MAX_BITS &&
-			  BITS < FUSE_MAX_BITS - 3 && D.fused_blocks[BITS] > 0 && shift0 >= next_bits && !g_no_fuse;
+			  BITS < FUSE_MAX_BITS - 3 && D.fused_blocks[BITS][next_bits] > 0 && shift0 >= next_bits && !g_no_fuse;
 	if (fuse) {
 		const size_t smem = H::SMEM + (size_t(H::NB + 32) << next_bits) * 4;
-		histogram_kernel<BITS, 256, true><<<D.sms * D.fused_blocks[BITS], 256, smem, st>>>(
+		histogram_kernel<BITS, 256, true><<<D.sms * D.fused_blocks[BITS][next_bits], 256, smem, st>>>(
 			c, level, origin, next_bits);
 	} else {
 		histogram_kernel<BITS, 256, false><<<D.sms * D.hist_blocks[BITS], 256, H::SMEM, st>>>(

@@ -36,7 +36,7 @@ constexpr uint32_t UNIT_CAP = LOCAL_CAP - 2;
 constexpr uint32_t TILE = MSB64_TILE;   // element slots per histogram/scatter tile
 constexpr uint32_t COPY_TILE = 8192;    // pairs per copy tile
 #ifndef MSB64_FUSE_MAX_BITS
-#define MSB64_FUSE_MAX_BITS 13
+#define MSB64_FUSE_MAX_BITS 14
 #endif
 constexpr int FUSE_MAX_BITS = MSB64_FUSE_MAX_BITS;   // level 0 + level 1 digit bits the fused histogram pass handles (4 << bits bytes of shared counters)
 

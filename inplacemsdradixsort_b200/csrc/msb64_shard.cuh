@@ -35,12 +35,18 @@ constexpr int SHARD_MAX_WORLD = ROUTE_MAX_DEST;          // 64
 constexpr int SHARD_MAX_BUCKETS = 256;                   // bucket ids are bytes
 constexpr int SHARD_BITS = 12;                           // first-round digit: the keys' top 12 bits
 constexpr int SHARD_SLOTS = (2 << SHARD_BITS) + 2;       // a histogram row: 2^13 counts (window round) + min + max
-constexpr int SHARD_SUBS = 16;                           // sub-ranges per destination (pipeline depth)
+constexpr int SHARD_SUBS = 32;                           // most sub-ranges per destination (pipeline depth)
+constexpr int SHARD_ROUTE_BUCKETS = 128;                 // most buckets the route pass is asked for
 
+// Sub-ranges per destination.  More of them shorten the wait for the first one and make the
+// sub-range sorts cheaper per pair (2^25 pairs need 14 bits = two 7-bit passes with a fused
+// level-1 histogram; 2^26 pairs need 8 + 7: a slower 8-bit pass and a separate histogram pass),
+// but every sort has a fixed cost (~0.1 ms) and the route pass slows down beyond 128 buckets
+// (16-pair runs): 32 sub-ranges up to 4 GPUs, 16 on 8.
 inline int shard_subs(int world)
 {
 	int subs = SHARD_SUBS;
-	while (world * subs > SHARD_MAX_BUCKETS) subs >>= 1;
+	while (subs > 1 && world * subs > SHARD_ROUTE_BUCKETS) subs >>= 1;
 	return subs;
 }
 

@@ -8,7 +8,7 @@ partition into per-node ranges -> every thread sorts its range; msb_64.c:1546-16
     1. every rank histograms the top 12 bits of its keys (+ min / max key)   (device kernel)
     2. the histograms are all-gathered                                       (NCCL, or gloo)
     3. every rank computes the same cut of the bin axis into world x 16 buckets -- ascending
-       key ranges of near-equal count, 16 sub-ranges per destination -- and from it every
+       key ranges of near-equal count, 16-32 sub-ranges per destination -- and from it every
        count and offset on every GPU (msb64_b200_shard_plan; a narrow key span gets a
        second histogram round on a window over [min, max])                   (host, C++)
     4. ONE local MSD pass at HBM speed groups the rank's pairs by bucket     (device kernel)

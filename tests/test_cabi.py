@@ -169,7 +169,10 @@ def test_shard_plan_host(msb, world):
     from inplacemsdradixsort_b200 import msb64
     lib = msb.load_library()
     subs = lib.msb64_b200_shard_subs(world)
-    assert subs >= 1 and world * subs <= 256 and (world > 16 or subs == 16)
+    want = 32
+    while want > 1 and world * want > 128:
+        want //= 2
+    assert subs == want
     rng = np.random.default_rng(world)
     per = 40_000
     ks = [rng.integers(0, 1 << 64, size=per + 13 * r, dtype=np.uint64) for r in range(world)]

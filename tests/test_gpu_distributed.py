@@ -91,7 +91,7 @@ def _oracle_sorted(oracle, keys, rids):
 @pytest.mark.parametrize("exchange", ["pipelined", "nccl"])
 @pytest.mark.parametrize("kind", ["uniform", "low24", "dup16", "sorted", "midbits", "skew", "equal", "outlier"])
 def test_sharded_sorter_single_gpu(gpu, oracle, kind, exchange):
-    """world = 1: the pipelined form still runs its bucket pass and the 16 sub-range sorts."""
+    """world = 1: the pipelined form still runs its bucket pass and the sub-range sorts."""
     import torch
     from inplacemsdradixsort_b200.distributed import ShardedSorter
     n = 200_003
