@@ -477,20 +477,33 @@ def main_b200(args):
             tt = torch.tensor([lt[k] for k in names], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t = dict(zip(names, (float(x) for x in tt)))
-            gbs = out_bytes / (t["exchange"] * 1e-3) / 1e9 if t["exchange"] > 0 else None
+            direct = torch.tensor([lt.get("pairs_stored_by_route") or 0], dtype=torch.int64, device=dev)
+            dist.all_reduce(direct, op=dist.ReduceOp.MAX)
+            direct_bytes = 16 * int(direct.item())
+            staged_bytes = out_bytes - direct_bytes
+            gbs = staged_bytes / (t["exchange"] * 1e-3) / 1e9 if t["exchange"] > 0 else None
+            # everything has left the GPU when the last copy is done: route pass + copies
+            whole = out_bytes / ((t["route"] + t["exchange"]) * 1e-3) / 1e9 if t["exchange"] > 0 else None
             line["exchange"] = {
                 "kind": "pipelined", "plan_ms": t["plan"], "route_ms": t["route"],
                 "exchange_ms": t["exchange"], "first_wait_ms": t["first_wait"], "sort_ms": t["sort"],
                 "step_ms": t["total"],
                 "exchange_hidden_ms": max(t["exchange"] - t["first_wait"], 0.0),
                 "exchange_hidden_frac": max(t["exchange"] - t["first_wait"], 0.0) / t["exchange"] if t["exchange"] > 0 else None,
-                "bytes_out_per_gpu": out_bytes, "out_GB/s_per_gpu": gbs,
+                "bytes_out_per_gpu": out_bytes,
+                "bytes_stored_by_route_kernel": direct_bytes,
+                "route_kernel_out_GB/s": direct_bytes / (t["route"] * 1e-3) / 1e9 if t["route"] > 0 else None,
+                "bytes_moved_by_copy_engines": staged_bytes, "copy_engines_out_GB/s": gbs,
+                "out_GB/s_per_gpu": whole,
                 "nvlink_peak_GB/s_per_direction": 900.0,
-                "frac_of_nvlink": gbs / 900.0 if gbs else None,
-                "note": "max over ranks, one timed step; plan = histogram + all-gather + host cut; route = local "
-                        "bucket pass; exchange = first to last outgoing copy (copy engines, NVLink); first_wait = "
-                        "main stream idle until sub-range 0 is complete; sort = the sub-range sorts (32 per GPU up to 4 GPUs, 16 on 8), running "
-                        "while the later sub-ranges are still travelling (exchange_hidden_ms of the exchange)",
+                "frac_of_nvlink": whole / 900.0 if whole else None,
+                "note": "max over ranks, one timed step; plan = histogram + all-gather + host cut; route = bucket "
+                        "pass, which stores the first quarter of every peer's sub-ranges straight into the peer's "
+                        "HBM over NVLink; exchange = first to last outgoing copy of the staged rest (copy engines, "
+                        "NVLink); out_GB/s_per_gpu = all outgoing bytes over route + exchange time; first_wait = main "
+                        "stream idle until sub-range 0 is complete; sort = the sub-range sorts (32 per GPU up to 4 "
+                        "GPUs, 16 on 8), running while the later sub-ranges are still travelling "
+                        "(exchange_hidden_ms of the exchange)",
             }
         else:
             tt = torch.tensor([lt["plan"], lt["exchange"], lt["barrier"], lt["local_sort"]],

@@ -257,9 +257,11 @@ int msb64_b200_ipc_close(void *mapped);
  *                                MSB64_ERR_CAPACITY (a rank would overflow; msb_64.c:1574-1578)
  *                                or 1: the keys share a long prefix, the shard's digit was moved
  *                                onto their real span -- histogram again (reset = 0), gather, plan;
- *   msb64_b200_shard_exchange_sort   enqueues, without synchronising: the local bucket pass,
- *                                the bucket-by-bucket copies into the peers' receive buffers
- *                                over NVLink with their completion flags, and the sub-range by
+ *   msb64_b200_shard_exchange_sort   enqueues, without synchronising: the bucket pass (which stores
+ *                                the first quarter of every peer's sub-ranges straight into the
+ *                                peer's receive buffer over NVLink and stages the rest locally),
+ *                                the bucket-by-bucket copies of the staged part into the peers'
+ *                                receive buffers with their completion flags, and the sub-range by
  *                                sub-range sorts of what arrives (NVLink and HBM work overlap).
  * Afterwards msb64_b200_shard_keys / _rids hold msb64_b200_shard_count pairs: this rank's key
  * range, ascending, every key <= every key of the next rank.  The arrays stay valid until
@@ -289,6 +291,8 @@ int msb64_b200_shard_exchange_sort(msb64_b200_shard *shard, const uint64_t *d_ke
 				   const uint64_t *d_rids, uint64_t n, void *stream, int timed);
 uint64_t msb64_b200_shard_count(const msb64_b200_shard *shard);
 uint64_t msb64_b200_shard_sent(const msb64_b200_shard *shard);	/* pairs the last step sent to other GPUs */
+uint64_t msb64_b200_shard_sent_direct(const msb64_b200_shard *shard);	/* ... of which the route kernel stored
+									   straight into the peers' memory */
 uint64_t msb64_b200_shard_recv_capacity(const msb64_b200_shard *shard);
 uint64_t *msb64_b200_shard_keys(msb64_b200_shard *shard);
 uint64_t *msb64_b200_shard_rids(msb64_b200_shard *shard);

@@ -248,10 +248,14 @@ route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, 
 // atomics for the ranks, one global atomicAdd per non-empty bucket on cursors[bucket], a
 // 2-byte source-slot permutation and a coalesced write-out.  Algorithmic traffic 32 B/pair.
 struct BucketOut {
-	uint64_t *keys[2];       // [0] staging, [1] the rank's own receive buffer
-	uint64_t *rids[2];
-	uint32_t own_first;      // buckets [own_first, own_first + own_count) go to [1]
-	uint32_t own_count;
+	// [d] = receive buffer of rank d (this process' mapping of it; [self] = the rank's own),
+	// [ROUTE_MAX_DEST] = the local staging buffer
+	uint64_t *keys[ROUTE_MAX_DEST + 1];
+	uint64_t *rids[ROUTE_MAX_DEST + 1];
+	uint32_t subs;       // buckets per destination
+	uint32_t ndirect;    // sub-ranges [0, ndirect) of every destination are stored straight into its receive
+			     // buffer, over NVLink for the peers: the fused compute + exchange part of the pass
+	uint32_t self;       // all buckets of this rank go straight to its own receive buffer
 };
 
 template <int NBK>
@@ -259,7 +263,8 @@ struct BucketCfg {
 	static constexpr int THREADS = 256;
 	static constexpr int ITEMS = TILE / THREADS;
 	static constexpr size_t SMEM = size_t(TILE) * 16 + size_t(TILE) * 2 + size_t(NBK + 32) * 4 + size_t(NBK) * 4
-				       + 64 * 4 + 16;
+				       + 64 * 4 + 16
+				       + size_t(ROUTE_MAX_DEST + 1) * 16 + NBK;        // output pointers by target, target of every bucket
 };
 
 template <int NBK>
@@ -277,11 +282,22 @@ bucket_route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int 
 	uint32_t *cnt = reinterpret_cast<uint32_t *>(sidx + TILE);            // [NBK + 32]
 	uint32_t *delta = cnt + NBK + 32;                                     // [NBK]
 	uint32_t *scratch = delta + NBK;                                      // [64]
-	uint64_t *bar = reinterpret_cast<uint64_t *>(scratch + 64);
+	uint64_t *bar = reinterpret_cast<uint64_t *>(scratch + 64);           // [2] (one used)
+	uint64_t **okeys = reinterpret_cast<uint64_t **>(bar + 2);            // [ROUTE_MAX_DEST + 1]
+	uint64_t **orids = okeys + ROUTE_MAX_DEST + 1;                        // [ROUTE_MAX_DEST + 1]
+	uint8_t *target = reinterpret_cast<uint8_t *>(orids + ROUTE_MAX_DEST + 1);   // [NBK] index into okeys / orids
 
 	const uint32_t tid = threadIdx.x, lane = lane_id();
 	const uint32_t ntiles = (n + TILE - 1) / TILE;
 	if (blockIdx.x >= ntiles) return;
+	for (uint32_t i = tid; i <= ROUTE_MAX_DEST; i += THREADS) {
+		okeys[i] = out.keys[i];
+		orids[i] = out.rids[i];
+	}
+	for (uint32_t b = tid; b < NBK; b += THREADS) {
+		const uint32_t d = b / out.subs, sub = b - d * out.subs;
+		target[b] = uint8_t(d < ROUTE_MAX_DEST && (d == out.self || sub < out.ndirect) ? d : ROUTE_MAX_DEST);
+	}
 	auto start_copy = [&](uint32_t t) {
 		if (t >= ntiles || (t + 1) * uint64_t(TILE) > n) return;
 		mbar_expect_tx(bar, TILE * 16);
@@ -347,10 +363,10 @@ bucket_route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int 
 			const uint64_t key = kin[s];
 			const uint64_t rid = rin[s];
 			const uint32_t b = bucket_of(key);
-			const uint32_t own = (b - out.own_first) < out.own_count ? 1u : 0u;
+			const uint32_t to = target[b];
 			const uint32_t at = delta[b] + i;
-			st_stream_u64(out.keys[own] + at, key);
-			st_stream_u64(out.rids[own] + at, rid);
+			st_stream_u64(okeys[to] + at, key);
+			st_stream_u64(orids[to] + at, rid);
 		}
 		__syncthreads();
 		for (uint32_t i = tid; i < NBK + 32; i += THREADS) cnt[i] = 0;
@@ -372,6 +388,17 @@ __global__ void shard_signal_kernel(const FlagDst dst, int world, int self, uint
 	if (d >= world || d == self) return;
 	__threadfence_system();
 	*reinterpret_cast<volatile uint32_t *>(dst.flag[d] + slot) = epoch;
+}
+// the same for the sub-ranges the route pass stored straight into the peers' memory: thread
+// (peer, lane, sub-range) raises that flag word; runs behind the route kernel in its stream
+__global__ void shard_signal_direct_kernel(const FlagDst dst, int world, int self, int subs, int ndirect, uint32_t epoch)
+{
+	__threadfence_system();
+	for (int i = threadIdx.x; i < world * 2 * ndirect; i += blockDim.x) {
+		const int d = i / (2 * ndirect), r = i - d * 2 * ndirect, lane = r / ndirect, sub = r - lane * ndirect;
+		if (d != self)
+			*reinterpret_cast<volatile uint32_t *>(dst.flag[d] + (size_t(lane) * subs + sub) * world + self) = epoch;
+	}
 }
 // wait: spins until every source's flag words of the given lanes of sub-range `sub` carry this epoch
 __global__ void shard_wait_kernel(const uint32_t *flags, int world, int self, int subs, int sub, int lanes,

@@ -43,6 +43,14 @@ constexpr int SHARD_ROUTE_BUCKETS = 128;                 // most buckets the rou
 // level-1 histogram; 2^26 pairs need 8 + 7: a slower 8-bit pass and a separate histogram pass),
 // but every sort has a fixed cost (~0.1 ms) and the route pass slows down beyond 128 buckets
 // (16-pair runs): 32 sub-ranges up to 4 GPUs, 16 on 8.
+// Sub-ranges of every destination that the route pass stores straight into the destination's
+// receive buffer (peer stores over NVLink, which has nothing else to do during the pass) instead
+// of staging them for the copy engines: a quarter of the exchange leaves the GPU inside the
+// route kernel at no extra HBM traffic, the first sub-ranges are complete when the pass ends
+// (the sorts start at once), and the copy engines -- which only get ~370-480 GB/s while the
+// sorts saturate HBM -- have less to move behind the sorts' back.
+inline int shard_direct(int world, int subs) { return world > 1 ? std::max(1, subs / 4) : 0; }
+
 inline int shard_subs(int world)
 {
 	int subs = SHARD_SUBS;
@@ -202,7 +210,7 @@ struct msb64_b200_shard {
 	cudaEvent_t tev[6] = {nullptr};                         // timing: start, routed, first sub-range in, sorted, exchange end x2
 	uint32_t epoch = 0;
 	ShardPlan plan;
-	uint64_t recv_total = 0, sent_total = 0;
+	uint64_t recv_total = 0, sent_total = 0, direct_total = 0;
 	uint64_t key_lo = 0, key_hi = ~0ull;
 	bool timed = false;
 	// only when the shard is driven by the host-array sort() of this process (msb64_b200.cu)
@@ -339,31 +347,44 @@ int shard_route_exchange_locked(msb64_b200_shard &S, const uint64_t *d_keys, con
 	}
 	if (S.timed) CUDA_TRY(cudaEventRecord(S.tev[0], st));
 
-	// 4. where every bucket of this source goes: foreign buckets side by side in the staging
-	//    buffer in the order they will travel (sub-range major), own buckets at their final place
+	// 4. where every bucket of this source goes: the first `ndirect` sub-ranges of every peer
+	//    straight into that peer's receive buffer (and all of the rank's own into its own), the
+	//    other foreign buckets side by side in the staging buffer in the order they will travel
+	//    (sub-range major)
+	const int ndirect = shard_direct(W, subs);
 	std::vector<uint32_t> cursors(SHARD_MAX_BUCKETS, 0);
 	std::vector<uint64_t> stage_off(nbk, 0);
-	uint64_t at = 0;
+	uint64_t at = 0, direct = 0;
 	for (int s = 0; s < subs; ++s)
 		for (int j = 1; j < W; ++j) {
 			const int d = (me + j) % W, b = d * subs + s;
-			stage_off[b] = at;
-			cursors[b] = uint32_t(at);
-			at += P.counts[size_t(me) * nbk + b];
+			const uint64_t cnt = P.counts[size_t(me) * nbk + b];
+			if (s < ndirect) {
+				cursors[b] = uint32_t(P.recv_offset(d, s, me));
+				direct += cnt;
+			} else {
+				stage_off[b] = at;
+				cursors[b] = uint32_t(at);
+				at += cnt;
+			}
 		}
-	S.sent_total = at;
+	S.sent_total = at + direct;
+	S.direct_total = direct;
 	for (int s = 0; s < subs; ++s) cursors[me * subs + s] = uint32_t(P.recv_offset(me, s, me));
 	CUDA_TRY(cudaMemcpyAsync(S.d_table, P.table.data(), P.table.size(), cudaMemcpyHostToDevice, st));
 	CUDA_TRY(cudaMemcpyAsync(S.d_cursors, cursors.data(), SHARD_MAX_BUCKETS * sizeof(uint32_t),
 				 cudaMemcpyHostToDevice, st));
+	FlagDst fd;
+	for (int d = 0; d < ROUTE_MAX_DEST; ++d) fd.flag[d] = S.peer_flags[d < W ? d : me];
 	if (n) {
 		BucketOut out;
-		out.keys[0] = S.stage_keys;
-		out.rids[0] = S.stage_rids;
-		out.keys[1] = S.recv_keys;
-		out.rids[1] = S.recv_rids;
-		out.own_first = uint32_t(me * subs);
-		out.own_count = uint32_t(subs);
+		for (int d = 0; d <= ROUTE_MAX_DEST; ++d) {
+			out.keys[d] = d < W ? S.peer_keys[d] : S.stage_keys;
+			out.rids[d] = d < W ? S.peer_rids[d] : S.stage_rids;
+		}
+		out.subs = uint32_t(subs);
+		out.ndirect = uint32_t(ndirect);
+		out.self = uint32_t(me);
 		int rc;
 		if (nbk <= 32) rc = launch_bucket_route<32>(D, d_keys, d_rids, n, P, S.d_table, S.d_cursors, out, st);
 		else if (nbk <= 64) rc = launch_bucket_route<64>(D, d_keys, d_rids, n, P, S.d_table, S.d_cursors, out, st);
@@ -371,18 +392,21 @@ int shard_route_exchange_locked(msb64_b200_shard &S, const uint64_t *d_keys, con
 		else rc = launch_bucket_route<256>(D, d_keys, d_rids, n, P, S.d_table, S.d_cursors, out, st);
 		if (rc) return rc;
 	}
+	if (W > 1) {
+		// the directly stored sub-ranges of this source are complete at every peer
+		shard_signal_direct_kernel<<<1, 256, 0, st>>>(fd, W, me, subs, ndirect, S.epoch);
+		g_launches += 1;
+	}
 	CUDA_TRY(cudaEventRecord(S.ev_routed, st));
 	if (S.timed) CUDA_TRY(cudaEventRecord(S.tev[1], st));
 
 	// 5. exchange on two side streams: lane 0 carries keys, lane 1 rids
 	if (W > 1) {
-		FlagDst fd;
-		for (int d = 0; d < ROUTE_MAX_DEST; ++d) fd.flag[d] = S.peer_flags[d < W ? d : me];
 		for (int x = 0; x < 2; ++x) {
 			cudaStream_t xs = S.xs[x];
 			CUDA_TRY(cudaStreamWaitEvent(xs, S.ev_routed, 0));
 			const uint64_t *stage = x ? S.stage_rids : S.stage_keys;
-			for (int s = 0; s < subs; ++s) {
+			for (int s = ndirect; s < subs; ++s) {
 				for (int j = 1; j < W; ++j) {
 					const int d = (me + j) % W, b = d * subs + s;
 					const uint64_t cnt = P.counts[size_t(me) * nbk + b];
@@ -647,6 +671,7 @@ int msb64_b200_shard_exchange_sort(msb64_b200_shard *S, const uint64_t *d_keys, 
 
 uint64_t msb64_b200_shard_count(const msb64_b200_shard *S) { return S ? S->recv_total : 0; }
 uint64_t msb64_b200_shard_sent(const msb64_b200_shard *S) { return S ? S->sent_total : 0; }
+uint64_t msb64_b200_shard_sent_direct(const msb64_b200_shard *S) { return S ? S->direct_total : 0; }
 uint64_t msb64_b200_shard_recv_capacity(const msb64_b200_shard *S) { return S ? S->recv_cap : 0; }
 uint64_t *msb64_b200_shard_keys(msb64_b200_shard *S) { return S ? S->recv_keys : nullptr; }
 uint64_t *msb64_b200_shard_rids(msb64_b200_shard *S) { return S ? S->recv_rids : nullptr; }

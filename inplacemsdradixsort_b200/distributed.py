@@ -11,9 +11,11 @@ partition into per-node ranges -> every thread sorts its range; msb_64.c:1546-16
        key ranges of near-equal count, 16-32 sub-ranges per destination -- and from it every
        count and offset on every GPU (msb64_b200_shard_plan; a narrow key span gets a
        second histogram round on a window over [min, max])                   (host, C++)
-    4. ONE local MSD pass at HBM speed groups the rank's pairs by bucket     (device kernel)
-    5. sub-range by sub-range the copy engines move the buckets into the destination GPUs'
-       receive buffers over NVLink (CUDA IPC peer memory) and raise a flag behind each
+    4. ONE MSD pass at HBM speed groups the rank's pairs by bucket; the first quarter of every
+       peer's sub-ranges it stores straight into that peer's receive buffer over NVLink
+       (fused compute + exchange), the rest into a local staging buffer       (device kernel)
+    5. sub-range by sub-range the copy engines move the staged buckets into the destination
+       GPUs' receive buffers over NVLink (CUDA IPC peer memory) and raise a flag behind each
     6. while sub-ranges s+1.. are still travelling, the destination sorts sub-range s with the
        single-GPU sort told its key range: NVLink and HBM work overlap.
 "peer"  one kernel routes a tile by destination and stores the runs straight into the peers'
@@ -328,7 +330,8 @@ class ShardedSorter:
             self.last_times = {"plan": ev[0].elapsed_time(ev[1]), "route": ms[0], "first_wait": ms[1],
                                "sort": ms[2], "exchange": ms[3], "step_device": ms[4],
                                "total": ev[0].elapsed_time(ev[2]), "pairs_received": total,
-                               "pairs_sent_to_peers": int(lib.msb64_b200_shard_sent(shard))}
+                               "pairs_sent_to_peers": int(lib.msb64_b200_shard_sent(shard)),
+                               "pairs_stored_by_route": int(lib.msb64_b200_shard_sent_direct(shard))}
         return self.recv_keys[:total], self.recv_rids[:total], total
 
     # -- peer-memory exchange: map every rank's receive buffers into this process

@@ -47,7 +47,7 @@ EXPORTS = (
     "msb64_b200_shard_connect_ipc", "msb64_b200_shard_connect_local", "msb64_b200_shard_slots",
     "msb64_b200_shard_subs", "msb64_b200_shard_histogram", "msb64_b200_shard_hist",
     "msb64_b200_shard_plan", "msb64_b200_shard_plan_host", "msb64_b200_shard_exchange_sort",
-    "msb64_b200_shard_count", "msb64_b200_shard_sent", "msb64_b200_shard_recv_capacity", "msb64_b200_shard_keys",
+    "msb64_b200_shard_count", "msb64_b200_shard_sent", "msb64_b200_shard_sent_direct", "msb64_b200_shard_recv_capacity", "msb64_b200_shard_keys",
     "msb64_b200_shard_rids", "msb64_b200_shard_key_range", "msb64_b200_shard_times",
 )
 
@@ -169,7 +169,7 @@ def load_library() -> C.CDLL:
     L.msb64_b200_shard_exchange_sort.restype = C.c_int
     L.msb64_b200_shard_exchange_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                                  C.c_void_p, C.c_int]
-    for name in ("count", "sent", "recv_capacity"):
+    for name in ("count", "sent", "sent_direct", "recv_capacity"):
         f = getattr(L, f"msb64_b200_shard_{name}")
         f.restype = C.c_uint64
         f.argtypes = [C.c_void_p]
