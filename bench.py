@@ -521,7 +521,13 @@ def main_b200(args):
             }
 
     # ---- roofline of the dominant kernel, from CUDA events inside this process
-    if rank == 0 or dist is None:
+    # (a single-GPU sort of one rank's share needs its own workspace: skipped where the sharded
+    # sort's buffers leave no room for it, e.g. 2^31 pairs per GPU)
+    room = torch.cuda.mem_get_info(dev)[0] > m.workspace_bytes(n) + (2 << 30) or dist is None
+    if (rank == 0 or dist is None) and not room:
+        line["roofline"] = None
+        line["kernels"] = {"note": "not re-measured: no room for a single-GPU workspace beside the sharded sort's buffers"}
+    if (rank == 0 or dist is None) and room:
         restore()
         torch.cuda.synchronize()
         phases = m.sort_device(keys.data_ptr(), rids.data_ptr(), n, stream=stream, timed=True)

@@ -49,7 +49,17 @@ constexpr int SHARD_ROUTE_BUCKETS = 128;                 // most buckets the rou
 // route kernel at no extra HBM traffic, the first sub-ranges are complete when the pass ends
 // (the sorts start at once), and the copy engines -- which only get ~370-480 GB/s while the
 // sorts saturate HBM -- have less to move behind the sorts' back.
-inline int shard_direct(int world, int subs) { return world > 1 ? std::max(1, subs / 4) : 0; }
+// MSB64_SHARD_DIRECT_EIGHTHS (developer switch): the fraction in eighths, 0..8.
+constexpr int SHARD_DIRECT_EIGHTHS = 2;
+inline int shard_direct(int world, int subs)
+{
+	static const int eighths = [] {
+		const char *v = getenv("MSB64_SHARD_DIRECT_EIGHTHS");
+		return v ? std::min(std::max(atoi(v), 0), 8) : SHARD_DIRECT_EIGHTHS;
+	}();
+	if (world < 2) return 0;
+	return eighths ? std::max(1, subs * eighths / 8) : 0;
+}
 
 inline int shard_subs(int world)
 {

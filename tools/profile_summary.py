@@ -46,14 +46,14 @@ def launches(path, out):
         t[0] += 1
         t[1] += ns
     whole = sum(v[1] for v in tot.values())
-    ours = sum(v[1] for k, v in tot.items() if re.match(r"(histogram|scatter|plan|local_sort(_packed)?|copy|init|route|digit_histogram)_kernel", k))
+    ours = sum(v[1] for k, v in tot.items() if re.match(r"(histogram|scatter|plan|local_sort(_packed)?|copy|init|route|bucket_route|tail|digit_histogram)_kernel", k))
     with open(out, "w") as f:
         f.write(f"# {os.path.basename(path)}: {len(rows)} launches, {whole / 1e6:.3f} ms of kernel time "
                 f"(ncu serialises launches and runs them cold; shares, not absolutes, carry over)\n")
         f.write(f"# share of the sort's own kernels: {100 * ours / whole:.1f}% (the rest: fill, check, torch copies)\n")
         f.write(f"{'kernel':48s} {'launches':>8s} {'total ms':>10s} {'share':>7s} {'share of sort':>14s}\n")
         for k, (n, ns) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-            mine = re.match(r"(histogram|scatter|plan|local_sort(_packed)?|copy|init|route|digit_histogram)_kernel", k)
+            mine = re.match(r"(histogram|scatter|plan|local_sort(_packed)?|copy|init|route|bucket_route|tail|digit_histogram)_kernel", k)
             f.write(f"{k:48s} {n:8d} {ns / 1e6:10.3f} {100 * ns / whole:6.1f}% "
                     f"{(100 * ns / ours if mine else 0):13.1f}%\n")
     return out
@@ -98,7 +98,8 @@ def main():
         path = os.path.join(ROOT, "profiles", "scatter_traffic.json")
         json.dump({"dram_bytes_per_launch": sum(b for b, _ in scatter) / len(scatter),
                    "launches": len(scatter), "source": f"ncu --set full, round {rnd}, "
-                   "dram__bytes_read.sum + dram__bytes_write.sum of the non-empty scatter launches"},
+                   "dram__bytes_read.sum + dram__bytes_write.sum of the non-empty scatter launches",
+                   "pairs": int(os.environ.get("MSB64_PROFILE_PAIRS", 1 << 30)), "workload": "uniform"},
                   open(path, "w"), indent=1)
         print(path)
 
