@@ -264,7 +264,7 @@ struct BucketCfg {
 	static constexpr int ITEMS = TILE / THREADS;
 	static constexpr size_t SMEM = size_t(TILE) * 16 + size_t(TILE) * 2 + size_t(NBK + 32) * 4 + size_t(NBK) * 4
 				       + 64 * 4 + 16
-				       + size_t(ROUTE_MAX_DEST + 1) * 16 + NBK;        // output pointers by target, target of every bucket
+				       + size_t(ROUTE_MAX_DEST + 1) * 16 + 2 * NBK;    // output pointers by target, target of every bucket, list of the peers' buckets
 };
 
 template <int NBK>
@@ -286,6 +286,8 @@ bucket_route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int 
 	uint64_t **okeys = reinterpret_cast<uint64_t **>(bar + 2);            // [ROUTE_MAX_DEST + 1]
 	uint64_t **orids = okeys + ROUTE_MAX_DEST + 1;                        // [ROUTE_MAX_DEST + 1]
 	uint8_t *target = reinterpret_cast<uint8_t *>(orids + ROUTE_MAX_DEST + 1);   // [NBK] index into okeys / orids
+	uint8_t *plist = target + NBK;                                        // [NBK] buckets stored into a peer's memory
+	__shared__ uint32_t s_npeer;
 
 	const uint32_t tid = threadIdx.x, lane = lane_id();
 	const uint32_t ntiles = (n + TILE - 1) / TILE;
@@ -297,6 +299,14 @@ bucket_route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int 
 	for (uint32_t b = tid; b < NBK; b += THREADS) {
 		const uint32_t d = b / out.subs, sub = b - d * out.subs;
 		target[b] = uint8_t(d < ROUTE_MAX_DEST && (d == out.self || sub < out.ndirect) ? d : ROUTE_MAX_DEST);
+	}
+	if (tid == 0) {
+		uint32_t np = 0;
+		for (uint32_t b = 0; b < NBK; ++b) {
+			const uint32_t d = b / out.subs, sub = b - d * out.subs;
+			if (d < ROUTE_MAX_DEST && d != out.self && sub < out.ndirect) plist[np++] = uint8_t(b);
+		}
+		s_npeer = np;
 	}
 	auto start_copy = [&](uint32_t t) {
 		if (t >= ntiles || (t + 1) * uint64_t(TILE) > n) return;
@@ -357,16 +367,40 @@ bucket_route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int 
 			if (d < NBK) sidx[cnt[d] + (dr[j] & RANK_MASK)] = uint16_t(((j >> 1) * THREADS + tid) * 2 + (j & 1));
 		}
 		__syncthreads();
+		// write-out.  Local targets (staging, the rank's own receive buffer): position i of the
+		// bucket-ordered tile goes to delta[bucket] + i, consecutive lanes to consecutive addresses.
 #pragma unroll 8
 		for (uint32_t i = tid; i < count; i += THREADS) {
 			const uint32_t s = sidx[i];
 			const uint64_t key = kin[s];
-			const uint64_t rid = rin[s];
 			const uint32_t b = bucket_of(key);
 			const uint32_t to = target[b];
-			const uint32_t at = delta[b] + i;
-			st_stream_u64(okeys[to] + at, key);
-			st_stream_u64(orids[to] + at, rid);
+			if (to == ROUTE_MAX_DEST || to == out.self) {
+				const uint32_t at = delta[b] + i;
+				st_stream_u64(okeys[to] + at, key);
+				st_stream_u64(orids[to] + at, rin[s]);
+			}
+		}
+		// Buckets that live in a peer's memory: nothing merges stores on their way over NVLink,
+		// so a warp takes a bucket's run and writes it in the DESTINATION's 256-byte windows
+		// (lane = element index mod 32): every store instruction is at most two 128-byte lines,
+		// whole ones except at the run's two ends.
+		{
+			const uint32_t npeer = s_npeer;
+			for (uint32_t q = tid >> 5; q < npeer; q += THREADS / 32) {
+				const uint32_t b = plist[q];
+				const uint32_t first = cnt[b];
+				const uint32_t len = (b + 1 < NBK ? cnt[b + 1] : total) - first;
+				if (!len) continue;
+				const uint32_t dl = delta[b], g0 = dl + first, g1 = g0 + len;
+				uint64_t *pk = okeys[target[b]], *pr = orids[target[b]];
+				for (uint32_t e = (g0 & ~31u) + lane; e < g1; e += 32)
+					if (e >= g0) {
+						const uint32_t s = sidx[e - dl];
+						st_stream_u64(pk + e, kin[s]);
+						st_stream_u64(pr + e, rin[s]);
+					}
+			}
 		}
 		__syncthreads();
 		for (uint32_t i = tid; i < NBK + 32; i += THREADS) cnt[i] = 0;
