@@ -165,6 +165,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(use), "window": window}
 
 
+def near_cpus(gpu_index: int):
+    """CPUs NVML names as closest to the GPU (intersected with what this process may use), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -601,7 +615,18 @@ def main_b200(args):
     # ---- end to end with host buffers
     if not args.no_e2e:
         cap = n if sorter is None else sorter.recv_cap
+        # a rank's host arrays belong on the NUMA node its GPU hangs off (the reference places
+        # every node's arrays with numa_alloc_onnode, msb_64.c:2302): run on that node's cores
+        # while the page-locked arrays are allocated, so that first touch puts them there
+        near = near_cpus(local_rank) if world > 1 else None
+        was = os.sched_getaffinity(0) if near else None
+        if near:
+            try:
+                os.sched_setaffinity(0, near)
+            except OSError:
+                near = None
         hk, hr = m.pinned(cap), m.pinned(cap)
+        line_numa = sorted(near)[:1] + sorted(near)[-1:] if near else None
         e2e_s = []
         got = n
         for i in range(args.e2e_steps + 1):
@@ -637,7 +662,11 @@ def main_b200(args):
         t = torch.tensor([sum(e2e_s) / len(e2e_s)], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if was:
+            os.sched_setaffinity(0, was)
         line["e2e"] = {"value": world * n / float(t.item()) / 1e9, "unit": UNIT,
+                       "host_arrays": ("page-locked, allocated on the cores nearest the rank's GPU (NVML cpu affinity), "
+                                       f"rank 0: cpus {line_numa[0]}-{line_numa[1]}" if line_numa else "page-locked"),
                        "h2d_bytes_per_step": 16 * n * world, "d2h_bytes_per_step": 16 * n * world,
                        "ms_per_step": float(t.item()) * 1e3, "steps": len(e2e_s),
                        "api": "sort() of include/msb64_b200.h with pinned host arrays" if sorter is None else
