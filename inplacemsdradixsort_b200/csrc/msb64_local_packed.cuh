@@ -99,7 +99,7 @@ local_sort_packed_kernel(const Ctx c, const uint64_t base_key)
 	uint64_t *bar = wred + 2 * WARPS;
 	__shared__ uint32_t s_nbig;
 
-	const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+	const uint32_t tid = threadIdx.x, lane = lane_id();
 	const uint32_t nunits = min(c.ctl->nunits, c.max_units);
 	if (blockIdx.x >= nunits) return;
 	if (tid == 0) {
@@ -154,16 +154,7 @@ local_sort_packed_kernel(const Ctx c, const uint64_t base_key)
 				vor |= e0 | e1;
 				vand &= e0 & e1;
 			}
-		{
-			const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(vor));
-			const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(vor >> 32));
-			const uint32_t alo = __reduce_and_sync(0xffffffffu, uint32_t(vand));
-			const uint32_t ahi = __reduce_and_sync(0xffffffffu, uint32_t(vand >> 32));
-			if (lane == 0) {
-				wred[warp] = (uint64_t(ohi) << 32) | olo;
-				wred[WARPS + warp] = (uint64_t(ahi) << 32) | alo;
-			}
-		}
+		or_and_warp_to_shared<WARPS>(vor, vand, wred);
 		__syncthreads();
 		// every thread is past the previous unit's write-out: its rids may be overwritten
 		if (tid == 0) {
@@ -175,16 +166,7 @@ local_sort_packed_kernel(const Ctx c, const uint64_t base_key)
 			if (tail)                                        // the window's last chunk: only the slots inside the array
 				for (uint32_t w = elems; w < a + size; ++w) rin[w] = src_rids[w];
 		}
-		{
-			const uint64_t o = lane < WARPS ? wred[lane] : 0ull;
-			const uint64_t d = lane < WARPS ? wred[WARPS + lane] : ~0ull;
-			const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(o));
-			const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(o >> 32));
-			const uint32_t alo = __reduce_and_sync(0xffffffffu, uint32_t(d));
-			const uint32_t ahi = __reduce_and_sync(0xffffffffu, uint32_t(d >> 32));
-			vor = (uint64_t(ohi) << 32) | olo;
-			vand = (uint64_t(ahi) << 32) | alo;
-		}
+		or_and_from_shared<WARPS>(wred, &vor, &vand);
 		const uint64_t diff = vor & ~vand;
 		uint64_t *out_keys = c.keys[0] + w0, *out_rids = c.rids[0] + w0;
 		// window chunk q home: slots outside the unit belong to the neighbours and stay untouched

@@ -57,6 +57,37 @@ constexpr size_t LOCAL_SMEM = size_t(LOCAL_CAP) * 16 + (size_t(LOCAL_NBINS) + 32
 			      + LOCAL_LIST_MAX * 4 + LOCAL_BIG_MAX * 4 + 64 * 4
 			      + 2 * (LOCAL_THREADS / 32) * 8;
 
+// OR and AND of one 64-bit value per thread over the block, in two steps around a barrier the
+// caller places (both local-sort kernels do other work between them): every warp leaves its
+// partial results in wred[0 .. WARPS) (OR) and wred[WARPS .. 2 WARPS) (AND) ...
+template <int WARPS>
+__device__ __forceinline__ void or_and_warp_to_shared(uint64_t vor, uint64_t vand, uint64_t *wred)
+{
+	const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(vor));
+	const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(vor >> 32));
+	const uint32_t alo = __reduce_and_sync(0xffffffffu, uint32_t(vand));
+	const uint32_t ahi = __reduce_and_sync(0xffffffffu, uint32_t(vand >> 32));
+	if (lane_id() == 0) {
+		wred[threadIdx.x >> 5] = (uint64_t(ohi) << 32) | olo;
+		wred[WARPS + (threadIdx.x >> 5)] = (uint64_t(ahi) << 32) | alo;
+	}
+}
+// ... and, behind the barrier, every warp folds them (the result is the same on all threads)
+template <int WARPS>
+__device__ __forceinline__ void or_and_from_shared(const uint64_t *wred, uint64_t *vor, uint64_t *vand)
+{
+	static_assert(WARPS <= 32, "one lane per warp result");
+	const uint32_t lane = lane_id();
+	const uint64_t o = lane < WARPS ? wred[lane] : 0ull;
+	const uint64_t a = lane < WARPS ? wred[WARPS + lane] : ~0ull;
+	const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(o));
+	const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(o >> 32));
+	const uint32_t alo = __reduce_and_sync(0xffffffffu, uint32_t(a));
+	const uint32_t ahi = __reduce_and_sync(0xffffffffu, uint32_t(a >> 32));
+	*vor = (uint64_t(ohi) << 32) | olo;
+	*vand = (uint64_t(ahi) << 32) | alo;
+}
+
 // Ascending compare-exchange network for any length (bitonic merges with the first
 // step mirrored, so that the missing tail behaves like +infinity).
 __device__ __forceinline__ void block_bitonic(uint64_t *k, uint64_t *r, const uint32_t n)
@@ -96,7 +127,7 @@ local_sort_kernel(const Ctx c, const uint64_t base_key)
 	uint64_t *wred = reinterpret_cast<uint64_t *>(scratch + 64);     // [2 * WARPS] OR, AND per warp
 	__shared__ uint32_t s_nbig;
 
-	const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+	const uint32_t tid = threadIdx.x, lane = lane_id();
 	const uint32_t nunits = min(c.ctl->nslow, c.max_units);          // this kernel's units sit at the back
 	const Unit *units = c.units + c.max_units - 1;                   // unit i is units[-i]
 
@@ -148,28 +179,10 @@ local_sort_kernel(const Ctx c, const uint64_t base_key)
 				vor |= k[j] - origin;
 				vand &= k[j] - origin;
 			}
-		{
-			const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(vor));
-			const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(vor >> 32));
-			const uint32_t alo = __reduce_and_sync(0xffffffffu, uint32_t(vand));
-			const uint32_t ahi = __reduce_and_sync(0xffffffffu, uint32_t(vand >> 32));
-			if (lane == 0) {
-				wred[warp] = (uint64_t(ohi) << 32) | olo;
-				wred[WARPS + warp] = (uint64_t(ahi) << 32) | alo;
-			}
-		}
+		or_and_warp_to_shared<WARPS>(vor, vand, wred);
 		__syncthreads();
-		uint64_t diff;
-		{
-			static_assert(WARPS <= 32, "one lane per warp result");
-			const uint64_t o = lane < WARPS ? wred[lane] : 0ull;
-			const uint64_t a = lane < WARPS ? wred[WARPS + lane] : ~0ull;
-			const uint32_t olo = __reduce_or_sync(0xffffffffu, uint32_t(o));
-			const uint32_t ohi = __reduce_or_sync(0xffffffffu, uint32_t(o >> 32));
-			const uint32_t alo = __reduce_and_sync(0xffffffffu, uint32_t(a));
-			const uint32_t ahi = __reduce_and_sync(0xffffffffu, uint32_t(a >> 32));
-			diff = ((uint64_t(ohi) << 32) | olo) & ~((uint64_t(ahi) << 32) | alo);
-		}
+		or_and_from_shared<WARPS>(wred, &vor, &vand);
+		const uint64_t diff = vor & ~vand;
 
 		if (diff == 0) {
 			// all keys equal: nothing to order, only bring the pairs home
