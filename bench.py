@@ -335,6 +335,12 @@ def main_reference(args):
 
 # ------------------------------------------------------------------ B200 arm
 def main_b200(args):
+    # stdout carries the one JSON line and nothing else: whatever libraries print while they
+    # initialise (NCCL announces its version on stdout) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import inplacemsdradixsort_b200 as m
@@ -683,7 +689,8 @@ def main_b200(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(),
                                     "kind": "reference", "sample": f"failed: {e}"}
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if sorter is not None:
         sorter.close()
     if dist is not None:
