@@ -92,6 +92,12 @@ def test_schedule_api(msb):
         with pytest.raises(msb.Msb64Error):
             msb.set_schedule(bad)
     assert msb.get_schedule(1 << 30)[:3] == [7, 6, 6]
+    # behind the digits uniform keys need: 7-bit tail digits (one cooperative launch, msb64_tail.cuh)
+    assert set(msb.get_schedule(1 << 30)[3:]) == {7}
+    # the sub-range sorts of the sharded path: 2^25 pairs in a 56-bit range take two 7-bit passes,
+    # 2^26 pairs in a 57-bit range 8 + 7 (msb64_shard.cuh)
+    assert msb.get_range_schedule(1 << 25, 0, (1 << 56) - 1)[0][:3] == [7, 7, 7]
+    assert msb.get_range_schedule(1 << 26, 0, (1 << 57) - 1)[0][:2] == [8, 7]
 
 
 def test_workspace_bytes(msb):
