@@ -258,9 +258,16 @@ struct BucketOut {
 	uint32_t self;       // all buckets of this rank go straight to its own receive buffer
 };
 
+#ifndef MSB64_BUCKET_THREADS
+#define MSB64_BUCKET_THREADS 256
+#endif
+#ifndef MSB64_BUCKET_MINB
+#define MSB64_BUCKET_MINB 3
+#endif
 template <int NBK>
 struct BucketCfg {
-	static constexpr int THREADS = 256;
+	static constexpr int THREADS = MSB64_BUCKET_THREADS;   // 256 x 3 blocks per SM: 5.58 ms per 2^30 pairs (512 x 2: 6.12 ms -- the opposite of the scatter pass)
+	static constexpr int MINB = MSB64_BUCKET_MINB;
 	static constexpr int ITEMS = TILE / THREADS;
 	static constexpr size_t SMEM = size_t(TILE) * 16 + size_t(TILE) * 2 + size_t(NBK + 32) * 4 + size_t(NBK) * 4
 				       + 64 * 4 + 16
@@ -268,7 +275,7 @@ struct BucketCfg {
 };
 
 template <int NBK>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(BucketCfg<NBK>::THREADS, BucketCfg<NBK>::MINB)
 bucket_route_kernel(const uint64_t *keys, const uint64_t *rids, uint32_t n, int shift, uint32_t tmask,
 		    uint32_t origin, const uint8_t *__restrict__ table, uint32_t *cursors, const BucketOut out)
 {

@@ -280,7 +280,7 @@ int launch_bucket_route(Device &D, const uint64_t *keys, const uint64_t *rids, u
 					      int(BucketCfg<NBK>::SMEM)));
 		configured[D.index] = true;
 	}
-	bucket_route_kernel<NBK><<<D.sms * 3, 256, BucketCfg<NBK>::SMEM, st>>>(
+	bucket_route_kernel<NBK><<<D.sms * BucketCfg<NBK>::MINB, BucketCfg<NBK>::THREADS, BucketCfg<NBK>::SMEM, st>>>(
 		keys, rids, uint32_t(n), P.shift, (1u << P.bits) - 1, uint32_t(P.origin), d_table, d_cursors, out);
 	g_launches += 1;
 	CUDA_TRY(cudaGetLastError());
