@@ -111,7 +111,7 @@ __device__ __forceinline__ void scatter_pass(const Ctx &c, const int level, cons
 	if (blockIdx.x >= ntiles) return;
 	// every segment of the level kept its place (degenerate digits: presorted keys, shared
 	// prefixes): nothing to walk through tile by tile
-	if (c.ctl->moved[level] == 0) return;
+	if (*reinterpret_cast<volatile uint32_t *>(&c.ctl->moved[level]) == 0) return;
 
 	// thread 0 only: descriptor of tile t into slot
 	auto fetch_desc = [&](uint32_t t, TileDesc *slot) {
