@@ -10,8 +10,9 @@
 // A block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Per tile of TILE pairs:
 //   0. keys and rids of the tile land in shared memory by two bulk asynchronous copies
 //      (cp.async.bulk + mbarrier, the non-tensor TMA path) issued by one thread: no
-//      register is tied up by a load in flight, so three blocks fit on an SM and cover
-//      one another's load latency; tile descriptors are read two tiles ahead;
+//      register is tied up by a load in flight, and the blocks of an SM (two of 512 threads
+//      in the sort's kernels, three of 256 in the tail kernel) cover one another's load
+//      latency; tile descriptors are read two tiles ahead;
 //   1. rank of every key among the tile's keys with the same digit: one shared-memory
 //      atomicAdd on the tile's bin counter (B200 sustains ~9 spread shared atomics
 //      per clock per SM, tools/microbench.cu; a ballot multisplit manages ~1); a warp
