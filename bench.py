@@ -567,7 +567,8 @@ def main_b200(args):
                 "bound": "hbm", "kernel": "scatter_kernel", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak,
                 # dram bytes per launch of the committed ncu --set full capture; only quoted when
-                # that capture was taken on this workload and size (it is not re-measured here)
+                # that capture was taken on this workload and size (it is not re-measured here;
+                # profiles/README.md says on which build it was taken)
                 "traffic": traffic.get("dram_bytes_per_launch") if same else None,
                 "traffic_source": (traffic.get("source") if same else
                                    "none for this workload / size (profiles/scatter_traffic.json holds 2^30 uniform)"),
